@@ -1,0 +1,204 @@
+/* ns2_b200.h — C ABI of libns2b200.so: the sm_100a kernels behind the NaturalSpeech2 denoiser hot path.
+ *
+ * The reference (lucidrains/naturalspeech2-pytorch @ 659bec7) has no FFI of its own; its boundary for this
+ * path is Python (nn.Module classes).  Each entry point below replaces the PyTorch library calls the
+ * reference makes at the cited lines (paths relative to the reference repo; ns2.py =
+ * naturalspeech2_pytorch/naturalspeech2_pytorch.py).  INTEGRATION.md shows the ctypes binding.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; all pointers are DEVICE pointers owned by the caller;
+ *  - every call is asynchronous on `stream` (a cudaStream_t passed as void*), never allocates device
+ *    memory, never synchronises, and is re-entrant;
+ *  - return value 0 = success, negative = error (ns2_last_error() gives a thread-local message);
+ *  - activations are token-major (batch, position, channel) with the channel contiguous;
+ *  - "bf16" buffers hold IEEE bfloat16, "f32" IEEE binary32, codes are int64 (as in the reference).
+ */
+#ifndef NS2_B200_H_
+#define NS2_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NS2_ABI_VERSION 1
+
+typedef void* ns2_stream_t; /* cudaStream_t */
+
+const char* ns2_last_error(void);
+int ns2_abi_version(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * 1. Segmented tcgen05 GEMM with fused epilogues.
+ *
+ * Computes, for every group g, batch b, position n and output channel j
+ *     acc_a[b,n,j] = sum over segments s with segs[s].acc == a, k < segs[s].k_len of
+ *                    A[b, n - segs[s].shift_units*dil[g], g*a_group_col_stride + segs[s].a_col_off + k]
+ *                  * B[g*b_group_row_stride + j, segs[s].b_col_off + k]
+ * where rows of A with a negative (or >= a_rows) position read as zero — this is the causal left padding
+ * of CausalConv1d (ns2.py:583-595): a k=3 dilated causal conv is three segments with shift_units 2,1,0.
+ * A Linear layer (nn.Linear: ns2.py:1021,1024,1051-1053,783) is one segment with shift 0.
+ *
+ * Epilogues (all accumulate in fp32):
+ *   NS2_EPI_BF16     out_bf16 = acc0 + bias
+ *   NS2_EPI_F32      out_f32  = acc0 + bias (+ resid_f32)           residual add of ns2.py:799,805,809
+ *   NS2_EPI_GEGLU    out_bf16[j] = gelu_erf(acc0[gate j] + bias) * (acc0[val j] + bias)   ns2.py:1004-1007;
+ *                    B rows must be packed so that each 256-row tile holds 128 value rows followed by
+ *                    the 128 matching gate rows (see pack_geglu_weight in the Python host code);
+ *                    `n` counts packed B rows (2x the number of output channels)
+ *   NS2_EPI_WAVENET  y = (acc0 + bias)*gamma[b,j] + beta[b,j]; out_bf16 = tanh(y)*sigmoid(y) + acc1 + bias1
+ *                    the WavenetResBlock body ns2.py:619-636 (acc0 = dilated conv, acc1 = res_conv);
+ *                    gamma = film[b*film_batch_stride + g*film_group_stride + j], beta = gamma + n;
+ *                    bias1 = bias + bias1_off.
+ * All k_len must be multiples of 64 unless the segment ends at the last column of A and B.
+ * ------------------------------------------------------------------------------------------------ */
+enum { NS2_EPI_BF16 = 0, NS2_EPI_F32 = 1, NS2_EPI_GEGLU = 2, NS2_EPI_WAVENET = 3 };
+#define NS2_GEMM_MAX_SEGS 8
+#define NS2_GEMM_MAX_GROUPS 8
+
+typedef struct ns2_gemm_seg {
+  int32_t a_col_off;   /* first A column of this segment (within the group's column window) */
+  int32_t b_col_off;   /* first B column (K index in the packed weight) */
+  int32_t k_len;       /* reduction length */
+  int32_t shift_units; /* row shift = shift_units * dil[group] */
+  int32_t acc;         /* accumulator id, 0 or 1 */
+} ns2_gemm_seg;
+
+typedef struct ns2_gemm_args {
+  const void* A;           /* bf16 (a_batches, a_rows, a_cols) */
+  int64_t a_row_stride;    /* elements */
+  int64_t a_batch_stride;  /* elements */
+  int32_t a_batches, a_rows, a_cols;
+  const void* B;           /* bf16 packed weights (b_rows, b_cols), K contiguous */
+  int64_t b_row_stride;    /* elements */
+  int32_t b_rows, b_cols;
+  int32_t n;               /* B rows (accumulator columns) per group */
+  int32_t groups;          /* >= 1; independent problems sharing the launch */
+  int32_t a_group_col_stride;
+  int32_t b_group_row_stride;
+  int32_t out_group_col_stride;
+  int32_t dil[NS2_GEMM_MAX_GROUPS];
+  int32_t num_segs;
+  ns2_gemm_seg segs[NS2_GEMM_MAX_SEGS];
+  int32_t epilogue;
+  const float* bias;       /* indexed like B rows (group offset = g*b_group_row_stride); may be NULL */
+  int32_t bias1_off;       /* WAVENET: offset of the res_conv bias inside `bias` */
+  void* out;               /* bf16 or f32, row (b*a_rows + n) */
+  int64_t out_row_stride;  /* elements */
+  const float* resid;      /* F32 epilogue: optional residual, same row indexing as out */
+  int64_t resid_row_stride;
+  const float* film;       /* WAVENET: FiLM table */
+  int64_t film_batch_stride;
+  int32_t film_group_stride;
+} ns2_gemm_args;
+
+int ns2_gemm(const ns2_gemm_args* args, ns2_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * 2. Non-causal, unmasked flash attention forward (Attend.forward, attend.py:112-155 with mask=None,
+ *    causal=False, dropout=0 — the only configuration the hot path uses).
+ *    q/k/v: bf16, head h lives in columns [h*64, h*64+64) of each row; dim_head must be 64.
+ *    out[b, i, h*64:(h+1)*64] = softmax_j(q_i . k_j * scale) @ v   (bf16)
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct ns2_attn_args {
+  const void* q; int64_t q_row_stride, q_batch_stride;
+  const void* k; int64_t k_row_stride, k_batch_stride;
+  const void* v; int64_t v_row_stride, v_batch_stride;
+  void* out;     int64_t o_row_stride, o_batch_stride;
+  int32_t batches, heads, q_len, kv_len, dim_head;
+  float scale;
+} ns2_attn_args;
+
+int ns2_attn_fwd(const ns2_attn_args* args, ns2_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * 3. RMSNorm (+ learned gamma) (+ FiLM) : RMSNorm.forward ns2.py:736-746.
+ *    out_bf16[r, :] = x[r,:] / max(||x[r,:]||_2, 1e-12) * sqrt(dim) * gamma * film_gamma[b] + film_beta[b]
+ *    gamma may be NULL (=1); film may be NULL (no FiLM); b = r / rows_per_batch;
+ *    film_gamma = film + b*film_batch_stride, film_beta = film_gamma + dim.
+ * ------------------------------------------------------------------------------------------------ */
+int ns2_rmsnorm_film(const float* x, int64_t x_row_stride, int64_t rows, int32_t dim,
+                     int32_t rows_per_batch, const float* gamma, const float* film,
+                     int64_t film_batch_stride, void* out_bf16, int64_t out_row_stride,
+                     ns2_stream_t stream);
+
+/* Same, fp32 output (PerceiverResampler.norm, ns2.py:566,579). */
+int ns2_rmsnorm_f32(const float* x, int64_t x_row_stride, int64_t rows, int32_t dim,
+                    const float* gamma, float* out, int64_t out_row_stride, ns2_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * 4. Small dense layers on the conditioning vector (M <= 64 rows), fp32 end to end.
+ *    ns2_time_cond : LearnedSinusoidalPosEmb + Linear + SiLU (ns2.py:108-120, 839-843)
+ *        out[b, :] = silu(W @ [t_b, sin(2 pi t_b w), cos(2 pi t_b w)] + bias),  W is (n_out, 2*half+1)
+ *    ns2_small_linear : out[b,:] = act(W @ x[b,:] + bias), act 0 = none, 1 = SiLU (ns2.py:858-862)
+ * ------------------------------------------------------------------------------------------------ */
+int ns2_time_cond(const float* times, int32_t batch, const float* freqs, int32_t half_dim,
+                  const float* W, const float* bias, int32_t n_out, float* out,
+                  int64_t out_row_stride, ns2_stream_t stream);
+int ns2_small_linear(const float* x, int64_t x_row_stride, int32_t batch, int32_t k, const float* W,
+                     const float* bias, int32_t n_out, int32_t act, float* out,
+                     int64_t out_row_stride, ns2_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * 5. Layout / cast helpers (what `rearrange` + autocast do in the reference, ns2.py:972-997).
+ *    ns2_cast_bf16        : out_bf16 = (bf16) (x [+ add]) ; add is broadcast over nothing (same shape) or NULL
+ *    ns2_mean_rows        : out[b,:] = mean over n of x[b,n,:]   (Reduce('b n d -> b d','mean'), ns2.py:859)
+ *    ns2_transpose_cast   : (B, C, L) f32 channel-first -> (B, L, C) bf16 token-major
+ * ------------------------------------------------------------------------------------------------ */
+int ns2_cast_bf16(const float* x, const float* add, int64_t count, void* out_bf16,
+                  ns2_stream_t stream);
+int ns2_mean_rows(const float* x, int32_t batch, int32_t n, int32_t dim, float* out,
+                  ns2_stream_t stream);
+int ns2_transpose_cast(const float* x, int32_t batch, int32_t channels, int32_t length,
+                       void* out_bf16, ns2_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * 6. Diffusion element-wise steps, fp32 (NaturalSpeech2.forward ns2.py:1621-1666; ddim_sample 1392-1429).
+ *    All take per-sample scalars as device arrays of length `batch`; `per_sample` = N*D elements.
+ *    ns2_q_sample   : x_t = alpha*x0 + sigma*noise ; target = alpha*noise - sigma*x0   (objective v)
+ *    ns2_mse_rows   : out[b] = mean((pred-target)^2) over the sample          (ns2.py:1646-1647);
+ *                     deterministic two-level reduction through caller-provided scratch
+ *    ns2_ddim_step  : x0 = alpha*x - sigma*v ; eps = (x - alpha*x0)/max(sigma,1e-10) ;
+ *                     x <- x0*alpha_next + eps*sigma_next                     (ns2.py:1420-1429)
+ *    ns2_cfg_combine: out = null + (cond - null)*scale                        (ns2.py:927)
+ * ------------------------------------------------------------------------------------------------ */
+#define NS2_MSE_SCRATCH_PER_SAMPLE 64
+int ns2_q_sample(const float* x0, const float* noise, const float* alpha, const float* sigma,
+                 int32_t batch, int64_t per_sample, float* x_t, float* target, ns2_stream_t stream);
+int ns2_mse_rows(const float* pred, const float* target, int32_t batch, int64_t per_sample,
+                 float* scratch /* batch * NS2_MSE_SCRATCH_PER_SAMPLE floats */, float* out,
+                 ns2_stream_t stream);
+int ns2_ddim_step(float* x, const float* v, const float* alpha, const float* sigma,
+                  const float* alpha_next, const float* sigma_next, int32_t batch,
+                  int64_t per_sample, ns2_stream_t stream);
+int ns2_cfg_combine(const float* cond, const float* null_, float scale, int64_t count, float* out,
+                    ns2_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * 7. Residual vector quantisation (Encodec RVQ encode/decode; third-party code reached from
+ *    ns2.py:1445,1611 via audiolm_pytorch.EncodecWrapper -> encodec ResidualVectorQuantizer).
+ *    ns2_rvq_prepare : codebooks f32 (Q, K, d) -> fp16 copy (Q, K, d) scaled by 2^-e_q, ||c||^2 f32 (Q, K),
+ *                      meta f32 (Q, 2) = {max_k ||c_k||, 2^e_q}
+ *    ns2_rvq_encode  : frames f32 (F, d) -> codes int64 (F, Q); residual chain in fp32, nearest
+ *                      codeword by exact squared L2 distance, ties -> lowest index.  d must be 128,
+ *                      K a multiple of 128.
+ *    ns2_rvq_decode  : emb f32 (F, d) = sum_q codebooks[q, codes[f,q], :]  (summed in order q = 0..Q-1)
+ * ------------------------------------------------------------------------------------------------ */
+int ns2_rvq_prepare(const float* codebooks, int32_t q, int32_t k, int32_t d, void* cb_f16,
+                    float* cb_norm2, float* cb_meta, ns2_stream_t stream);
+int ns2_rvq_encode(const float* frames, int64_t num_frames, int32_t d, const float* codebooks,
+                   const void* cb_f16, const float* cb_norm2, const float* cb_meta, int32_t q,
+                   int32_t k, int64_t* codes,
+                   int64_t* stats /* optional 3 counters {lookups, near-ties re-scored, full scans} */,
+                   ns2_stream_t stream);
+int ns2_rvq_decode(const int64_t* codes, int64_t num_frames, int32_t q, int32_t k, int32_t d,
+                   const float* codebooks, float* emb, ns2_stream_t stream);
+
+/* Number of kernel launches issued through this library since load (for bench.py's gpu_launches). */
+int64_t ns2_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NS2_B200_H_ */

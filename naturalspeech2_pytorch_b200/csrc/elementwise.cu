@@ -1,0 +1,452 @@
+// HBM-bound kernels of the denoiser step: RMSNorm(+FiLM), conditioning-vector layers, casts/layout,
+// and the diffusion element-wise updates.  All are coalesced 128-bit load/store kernels with warp-shuffle
+// row reductions; none of them belongs on tensor cores.  See include/ns2_b200.h sections 3-6 for the
+// reference lines each one replaces.
+#include "ptx.cuh"
+#include "host_common.h"
+#include "../../include/ns2_b200.h"
+
+#include <atomic>
+
+namespace ns2 {
+
+std::atomic<long long> g_launches{0};
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// RMSNorm (+gamma) (+FiLM): one warp per row, the row stays in registers between the reduction and the
+// scaled write (single HBM read of x, single write of the result).  DIM = 32 * 4 * VEC.
+// ------------------------------------------------------------------------------------------------
+template <int VEC, bool OUT_BF16>
+__global__ void __launch_bounds__(256) rmsnorm_kernel(const float* __restrict__ x, long long x_rs,
+                                                      long long rows, int dim, int rows_per_batch,
+                                                      const float* __restrict__ gamma,
+                                                      const float* __restrict__ film, long long film_bs,
+                                                      void* __restrict__ out, long long out_rs) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long row = static_cast<long long>(blockIdx.x) * 8 + warp;
+  if (row >= rows) return;
+  const float4* xp = reinterpret_cast<const float4*>(x + row * x_rs);
+  float4 v[VEC];
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    v[i] = __ldg(xp + i * 32 + lane);
+    ss += v[i].x * v[i].x + v[i].y * v[i].y + v[i].z * v[i].z + v[i].w * v[i].w;
+  }
+  ss = warp_sum(ss);
+  // F.normalize: x / max(||x||, eps), eps = 1e-12; then * sqrt(dim)   (ns2.py:738)
+  const float inv = sqrtf(static_cast<float>(dim)) / fmaxf(sqrtf(ss), 1e-12f);
+  const float* fg = nullptr;
+  if (film != nullptr) fg = film + (row / rows_per_batch) * film_bs;
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    const int c4 = i * 32 + lane;
+    float4 o = make_float4(v[i].x * inv, v[i].y * inv, v[i].z * inv, v[i].w * inv);
+    if (gamma != nullptr) {
+      const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + c4);
+      o.x *= g.x; o.y *= g.y; o.z *= g.z; o.w *= g.w;
+    }
+    if (fg != nullptr) {
+      const float4 g = __ldg(reinterpret_cast<const float4*>(fg) + c4);
+      const float4 b = __ldg(reinterpret_cast<const float4*>(fg + dim) + c4);
+      o.x = o.x * g.x + b.x; o.y = o.y * g.y + b.y; o.z = o.z * g.z + b.z; o.w = o.w * g.w + b.w;
+    }
+    if constexpr (OUT_BF16) {
+      uint2 w;
+      w.x = pack_bf16x2(o.x, o.y);
+      w.y = pack_bf16x2(o.z, o.w);
+      reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(out) + row * out_rs)[c4] = w;
+    } else {
+      reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + row * out_rs)[c4] = o;
+    }
+  }
+}
+
+template <bool OUT_BF16>
+static int launch_rmsnorm(const float* x, long long x_rs, long long rows, int dim, int rows_per_batch,
+                          const float* gamma, const float* film, long long film_bs, void* out,
+                          long long out_rs, cudaStream_t stream) {
+  NS2_REQUIRE(x && out && rows > 0, "rmsnorm: NULL or empty input");
+  NS2_REQUIRE(dim % 128 == 0 && dim <= 1024, "rmsnorm: dim=%d must be a multiple of 128, <= 1024", dim);
+  NS2_REQUIRE(x_rs % 4 == 0 && out_rs % 4 == 0 && film_bs % 4 == 0, "rmsnorm: strides must be 16B-aligned");
+  const unsigned grid = static_cast<unsigned>((rows + 7) / 8);
+#define NS2_RMS_CASE(V)                                                                         \
+  case V:                                                                                       \
+    rmsnorm_kernel<V, OUT_BF16><<<grid, 256, 0, stream>>>(x, x_rs, rows, dim, rows_per_batch,   \
+                                                          gamma, film, film_bs, out, out_rs);   \
+    break;
+  switch (dim / 128) {
+    NS2_RMS_CASE(1) NS2_RMS_CASE(2) NS2_RMS_CASE(3) NS2_RMS_CASE(4) NS2_RMS_CASE(5) NS2_RMS_CASE(6)
+    NS2_RMS_CASE(7) NS2_RMS_CASE(8)
+  }
+#undef NS2_RMS_CASE
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  NS2_CUDA_CHECK(cudaGetLastError());
+  return kOk;
+}
+
+// ------------------------------------------------------------------------------------------------
+// small dense layers on the conditioning vector: one warp per output feature, all (<= 64) batch rows at
+// once so the weight row is read exactly once.
+// ------------------------------------------------------------------------------------------------
+constexpr int kMaxSmallBatch = 64;
+
+__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + expf(-x)); }
+
+// If `freqs` is non-NULL the input row is the learned-sinusoidal embedding of x[b] (a scalar time):
+// [t, sin(2 pi t w_0..half-1), cos(2 pi t w_0..half-1)], k = 2*half + 1   (ns2.py:108-120).
+__global__ void __launch_bounds__(256) small_linear_kernel(const float* __restrict__ x, long long x_rs,
+                                                           int batch, int k,
+                                                           const float* __restrict__ freqs,
+                                                           const float* __restrict__ W,
+                                                           const float* __restrict__ bias, int n_out,
+                                                           int act, float* __restrict__ out,
+                                                           long long out_rs) {
+  extern __shared__ float xs[];  // (batch, k)
+  if (freqs == nullptr) {
+    for (int i = threadIdx.x; i < batch * k; i += blockDim.x) xs[i] = x[(i / k) * x_rs + (i % k)];
+  } else {
+    const int half = (k - 1) / 2;
+    for (int i = threadIdx.x; i < batch * k; i += blockDim.x) {
+      const int b = i / k, c = i % k;
+      const float t = x[b];
+      float v = t;
+      if (c > 0) {
+        // same association order as the reference: ((t * w) * 2) * pi   (ns2.py:117)
+        const float fr = t * freqs[(c - 1) % half] * 2.0f * 3.14159265358979323846f;
+        v = (c - 1 < half) ? sinf(fr) : cosf(fr);
+      }
+      xs[i] = v;
+    }
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int j = blockIdx.x * 8 + warp;
+  if (j >= n_out) return;
+  const float* w = W + static_cast<long long>(j) * k;
+  for (int b0 = 0; b0 < batch; b0 += 8) {
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int kk = lane; kk < k; kk += 32) {
+      const float wv = __ldg(w + kk);
+#pragma unroll
+      for (int b = 0; b < 8; ++b)
+        if (b0 + b < batch) acc[b] += wv * xs[(b0 + b) * k + kk];
+    }
+#pragma unroll
+    for (int b = 0; b < 8; ++b) {
+      const float s = warp_sum(acc[b]);
+      if (lane == 0 && b0 + b < batch) {
+        float r = s + (bias ? bias[j] : 0.f);
+        if (act == 1) r = silu_f(r);
+        out[(b0 + b) * out_rs + j] = r;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// casts and layout
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) cast_bf16_kernel(const float4* __restrict__ x,
+                                                        const float4* __restrict__ add, long long n4,
+                                                        uint2* __restrict__ out) {
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float4 v = __ldg(x + i);
+    if (add != nullptr) {
+      const float4 a = __ldg(add + i);
+      v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
+    }
+    uint2 w;
+    w.x = pack_bf16x2(v.x, v.y);
+    w.y = pack_bf16x2(v.z, v.w);
+    out[i] = w;
+  }
+}
+
+__global__ void __launch_bounds__(256) mean_rows_kernel(const float* __restrict__ x, int n, int dim,
+                                                        float* __restrict__ out) {
+  const int b = blockIdx.y;
+  const int d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= dim) return;
+  const float* p = x + static_cast<long long>(b) * n * dim + d;
+  float s = 0.f;
+  for (int i = 0; i < n; ++i) s += p[static_cast<long long>(i) * dim];
+  out[static_cast<long long>(b) * dim + d] = s / static_cast<float>(n);
+}
+
+// (B, C, L) f32 -> (B, L, C) bf16 through a 32x32 shared tile (coalesced on both sides)
+__global__ void __launch_bounds__(256) transpose_cast_kernel(const float* __restrict__ x, int C, int L,
+                                                             __nv_bfloat16* __restrict__ out) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int l0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  const float* xb = x + static_cast<long long>(b) * C * L;
+  __nv_bfloat16* ob = out + static_cast<long long>(b) * C * L;
+  for (int j = ty; j < 32; j += 8) {
+    const int c = c0 + j, l = l0 + tx;
+    tile[j][tx] = (c < C && l < L) ? xb[static_cast<long long>(c) * L + l] : 0.f;
+  }
+  __syncthreads();
+  for (int j = ty; j < 32; j += 8) {
+    const int l = l0 + j, c = c0 + tx;
+    if (c < C && l < L) ob[static_cast<long long>(l) * C + c] = __float2bfloat16_rn(tile[tx][j]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// diffusion element-wise steps
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) q_sample_kernel(const float4* __restrict__ x0,
+                                                       const float4* __restrict__ noise,
+                                                       const float* __restrict__ alpha,
+                                                       const float* __restrict__ sigma,
+                                                       long long per4, float4* __restrict__ xt,
+                                                       float4* __restrict__ target) {
+  const int b = blockIdx.y;
+  const float a = alpha[b], s = sigma[b];
+  const long long base = static_cast<long long>(b) * per4;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < per4;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float4 x = __ldg(x0 + base + i), e = __ldg(noise + base + i);
+    xt[base + i] = make_float4(a * x.x + s * e.x, a * x.y + s * e.y, a * x.z + s * e.z, a * x.w + s * e.w);
+    if (target != nullptr)
+      target[base + i] =
+          make_float4(a * e.x - s * x.x, a * e.y - s * x.y, a * e.z - s * x.z, a * e.w - s * x.w);
+  }
+}
+
+// per-sample mean squared error; deterministic two-level reduction (fixed grid, no atomics on floats)
+constexpr int kMseBlocks = 64;
+__global__ void __launch_bounds__(256) mse_partial_kernel(const float4* __restrict__ pred,
+                                                          const float4* __restrict__ target,
+                                                          long long per4, float* __restrict__ partial) {
+  const int b = blockIdx.y;
+  const long long base = static_cast<long long>(b) * per4;
+  float s = 0.f;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < per4;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float4 p = __ldg(pred + base + i), t = __ldg(target + base + i);
+    const float dx = p.x - t.x, dy = p.y - t.y, dz = p.z - t.z, dw = p.w - t.w;
+    s += dx * dx + dy * dy + dz * dz + dw * dw;
+  }
+  __shared__ float red[8];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < 8 ? red[threadIdx.x] : 0.f;
+    v = warp_sum(v);
+    if (threadIdx.x == 0) partial[b * kMseBlocks + blockIdx.x] = v;
+  }
+}
+__global__ void mse_final_kernel(const float* __restrict__ partial, long long per_sample,
+                                 float* __restrict__ out) {
+  const int b = blockIdx.x;
+  float v = threadIdx.x < kMseBlocks ? partial[b * kMseBlocks + threadIdx.x] : 0.f;
+  __shared__ float red[2];
+  v = warp_sum(v);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) out[b] = (red[0] + red[1]) / static_cast<float>(per_sample);
+}
+
+__global__ void __launch_bounds__(256) ddim_step_kernel(float4* __restrict__ x,
+                                                        const float4* __restrict__ v,
+                                                        const float* __restrict__ alpha,
+                                                        const float* __restrict__ sigma,
+                                                        const float* __restrict__ alpha_next,
+                                                        const float* __restrict__ sigma_next,
+                                                        long long per4) {
+  const int b = blockIdx.y;
+  const float a = alpha[b], s = sigma[b], an = alpha_next[b], sn = sigma_next[b];
+  const float s_safe = fmaxf(s, 1e-10f);  // safe_div (ns2.py:1122-1123)
+  const long long base = static_cast<long long>(b) * per4;
+  auto upd = [&](float xv, float vv) {
+    const float x0 = a * xv - s * vv;           // ns2.py:1421
+    const float eps = (xv - a * x0) / s_safe;   // ns2.py:1425
+    return x0 * an + eps * sn;                  // ns2.py:1429
+  };
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < per4;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float4 xv = x[base + i], vv = __ldg(v + base + i);
+    x[base + i] = make_float4(upd(xv.x, vv.x), upd(xv.y, vv.y), upd(xv.z, vv.z), upd(xv.w, vv.w));
+  }
+}
+
+__global__ void __launch_bounds__(256) cfg_combine_kernel(const float4* __restrict__ c,
+                                                          const float4* __restrict__ n, float scale,
+                                                          long long n4, float4* __restrict__ out) {
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float4 a = __ldg(c + i), b = __ldg(n + i);
+    out[i] = make_float4(b.x + (a.x - b.x) * scale, b.y + (a.y - b.y) * scale,
+                         b.z + (a.z - b.z) * scale, b.w + (a.w - b.w) * scale);
+  }
+}
+
+static cudaError_t configure_small_linear() {
+  static bool configured = false;
+  if (configured) return cudaSuccess;
+  cudaError_t e = cudaFuncSetAttribute(small_linear_kernel,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  configured = (e == cudaSuccess);
+  return e;
+}
+
+static unsigned grid_for(long long n4) {
+  long long g = (n4 + 255) / 256;
+  const long long cap = static_cast<long long>(num_sms()) * 8;
+  return static_cast<unsigned>(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+}  // namespace ns2
+
+using namespace ns2;
+
+extern "C" {
+
+int64_t ns2_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int ns2_rmsnorm_film(const float* x, int64_t x_row_stride, int64_t rows, int32_t dim,
+                     int32_t rows_per_batch, const float* gamma, const float* film,
+                     int64_t film_batch_stride, void* out_bf16, int64_t out_row_stride,
+                     ns2_stream_t stream) {
+  NS2_REQUIRE(rows_per_batch > 0, "rmsnorm_film: rows_per_batch must be positive");
+  return launch_rmsnorm<true>(x, x_row_stride, rows, dim, rows_per_batch, gamma, film,
+                              film_batch_stride, out_bf16, out_row_stride,
+                              static_cast<cudaStream_t>(stream));
+}
+
+int ns2_rmsnorm_f32(const float* x, int64_t x_row_stride, int64_t rows, int32_t dim,
+                    const float* gamma, float* out, int64_t out_row_stride, ns2_stream_t stream) {
+  return launch_rmsnorm<false>(x, x_row_stride, rows, dim, 1, gamma, nullptr, 0, out, out_row_stride,
+                               static_cast<cudaStream_t>(stream));
+}
+
+int ns2_small_linear(const float* x, int64_t x_row_stride, int32_t batch, int32_t k, const float* W,
+                     const float* bias, int32_t n_out, int32_t act, float* out,
+                     int64_t out_row_stride, ns2_stream_t stream) {
+  NS2_REQUIRE(x && W && out, "small_linear: NULL pointer");
+  NS2_REQUIRE(batch > 0 && batch <= kMaxSmallBatch, "small_linear: batch=%d must be in [1,%d]", batch,
+              kMaxSmallBatch);
+  const size_t smem = static_cast<size_t>(batch) * k * sizeof(float);
+  NS2_REQUIRE(smem <= 200 * 1024, "small_linear: batch*k=%d too large for shared memory", batch * k);
+  NS2_CUDA_CHECK(configure_small_linear());
+  small_linear_kernel<<<(n_out + 7) / 8, 256, smem, static_cast<cudaStream_t>(stream)>>>(
+      x, x_row_stride, batch, k, nullptr, W, bias, n_out, act, out, out_row_stride);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  NS2_CUDA_CHECK(cudaGetLastError());
+  return kOk;
+}
+
+int ns2_time_cond(const float* times, int32_t batch, const float* freqs, int32_t half_dim,
+                  const float* W, const float* bias, int32_t n_out, float* out,
+                  int64_t out_row_stride, ns2_stream_t stream) {
+  NS2_REQUIRE(times && freqs && W && out, "time_cond: NULL pointer");
+  NS2_REQUIRE(batch > 0 && batch <= kMaxSmallBatch, "time_cond: batch=%d must be in [1,%d]", batch,
+              kMaxSmallBatch);
+  const int k = 2 * half_dim + 1;
+  const size_t smem = static_cast<size_t>(batch) * k * sizeof(float);
+  NS2_REQUIRE(smem <= 200 * 1024, "time_cond: batch*k=%d too large for shared memory", batch * k);
+  NS2_CUDA_CHECK(configure_small_linear());
+  small_linear_kernel<<<(n_out + 7) / 8, 256, smem, static_cast<cudaStream_t>(stream)>>>(
+      times, 1, batch, k, freqs, W, bias, n_out, /*SiLU*/ 1, out, out_row_stride);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  NS2_CUDA_CHECK(cudaGetLastError());
+  return kOk;
+}
+
+int ns2_cast_bf16(const float* x, const float* add, int64_t count, void* out_bf16,
+                  ns2_stream_t stream) {
+  NS2_REQUIRE(x && out_bf16 && count > 0 && count % 4 == 0, "cast_bf16: count must be a multiple of 4");
+  const long long n4 = count / 4;
+  cast_bf16_kernel<<<grid_for(n4), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const float4*>(x), reinterpret_cast<const float4*>(add), n4,
+      reinterpret_cast<uint2*>(out_bf16));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  NS2_CUDA_CHECK(cudaGetLastError());
+  return kOk;
+}
+
+int ns2_mean_rows(const float* x, int32_t batch, int32_t n, int32_t dim, float* out,
+                  ns2_stream_t stream) {
+  NS2_REQUIRE(x && out && batch > 0 && n > 0 && dim > 0, "mean_rows: bad arguments");
+  dim3 grid((dim + 255) / 256, batch);
+  mean_rows_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, n, dim, out);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  NS2_CUDA_CHECK(cudaGetLastError());
+  return kOk;
+}
+
+int ns2_transpose_cast(const float* x, int32_t batch, int32_t channels, int32_t length,
+                       void* out_bf16, ns2_stream_t stream) {
+  NS2_REQUIRE(x && out_bf16 && batch > 0 && channels > 0 && length > 0, "transpose_cast: bad arguments");
+  dim3 grid((length + 31) / 32, (channels + 31) / 32, batch);
+  transpose_cast_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, channels, length, reinterpret_cast<__nv_bfloat16*>(out_bf16));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  NS2_CUDA_CHECK(cudaGetLastError());
+  return kOk;
+}
+
+int ns2_q_sample(const float* x0, const float* noise, const float* alpha, const float* sigma,
+                 int32_t batch, int64_t per_sample, float* x_t, float* target, ns2_stream_t stream) {
+  NS2_REQUIRE(x0 && noise && alpha && sigma && x_t, "q_sample: NULL pointer");
+  NS2_REQUIRE(per_sample % 4 == 0 && batch > 0, "q_sample: per_sample must be a multiple of 4");
+  dim3 grid(grid_for(per_sample / 4) / (batch > 8 ? 4 : 1) + 1, batch);
+  q_sample_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const float4*>(x0), reinterpret_cast<const float4*>(noise), alpha, sigma,
+      per_sample / 4, reinterpret_cast<float4*>(x_t), reinterpret_cast<float4*>(target));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  NS2_CUDA_CHECK(cudaGetLastError());
+  return kOk;
+}
+
+int ns2_mse_rows(const float* pred, const float* target, int32_t batch, int64_t per_sample,
+                 float* partial, float* out, ns2_stream_t stream) {
+  NS2_REQUIRE(pred && target && out && partial, "mse_rows: NULL pointer");
+  NS2_REQUIRE(per_sample % 4 == 0 && batch > 0, "mse_rows: bad sizes");
+  dim3 grid(kMseBlocks, batch);
+  mse_partial_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const float4*>(pred), reinterpret_cast<const float4*>(target), per_sample / 4,
+      partial);
+  mse_final_kernel<<<batch, 64, 0, static_cast<cudaStream_t>(stream)>>>(partial, per_sample, out);
+  g_launches.fetch_add(2, std::memory_order_relaxed);
+  NS2_CUDA_CHECK(cudaGetLastError());
+  return kOk;
+}
+
+int ns2_ddim_step(float* x, const float* v, const float* alpha, const float* sigma,
+                  const float* alpha_next, const float* sigma_next, int32_t batch,
+                  int64_t per_sample, ns2_stream_t stream) {
+  NS2_REQUIRE(x && v && alpha && sigma && alpha_next && sigma_next, "ddim_step: NULL pointer");
+  NS2_REQUIRE(per_sample % 4 == 0 && batch > 0, "ddim_step: per_sample must be a multiple of 4");
+  dim3 grid(grid_for(per_sample / 4) / (batch > 8 ? 4 : 1) + 1, batch);
+  ddim_step_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<float4*>(x), reinterpret_cast<const float4*>(v), alpha, sigma, alpha_next,
+      sigma_next, per_sample / 4);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  NS2_CUDA_CHECK(cudaGetLastError());
+  return kOk;
+}
+
+int ns2_cfg_combine(const float* cond, const float* null_, float scale, int64_t count, float* out,
+                    ns2_stream_t stream) {
+  NS2_REQUIRE(cond && null_ && out && count % 4 == 0, "cfg_combine: bad arguments");
+  cfg_combine_kernel<<<grid_for(count / 4), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const float4*>(cond), reinterpret_cast<const float4*>(null_), scale, count / 4,
+      reinterpret_cast<float4*>(out));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  NS2_CUDA_CHECK(cudaGetLastError());
+  return kOk;
+}
+
+}  // extern "C"

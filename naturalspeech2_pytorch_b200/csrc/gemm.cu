@@ -1,0 +1,446 @@
+// Segmented tcgen05 GEMM for sm_100a with fused epilogues (see include/ns2_b200.h, section 1).
+//
+// One persistent CTA per SM, 256 threads, warp-specialised:
+//   warp 0     TMA producer: A tile (128 positions x 64 channels, 3-D map so that shifted rows of a causal
+//              conv that fall before position 0 are zero-filled by the TMA unit) + B tile (BN x 64)
+//   warp 1     tcgen05.mma issuer (one elected lane), accumulators in TMEM, double-buffered across tiles
+//   warp 2     TMEM allocator
+//   warps 4-7  epilogue: tcgen05.ld -> registers -> bias / residual / GEGLU / FiLM+gate -> global
+// Three pipelines: smem ring (full/empty mbarriers, TMA <-> MMA), TMEM double buffer (tmem_full/empty,
+// MMA <-> epilogue), static round-robin tile scheduler (n fastest so co-resident CTAs share A rows in L2).
+//
+// Replaces, in the reference: nn.Linear GEMMs (ns2.py:1021,1024,1051-1053,783,613,731) and
+// CausalConv1d (ns2.py:583-595) incl. the WavenetResBlock body (ns2.py:619-636) and GEGLU (1004-1007).
+#include "ptx.cuh"
+#include "host_common.h"
+#include "../../include/ns2_b200.h"
+
+#include <atomic>
+
+namespace ns2 {
+
+extern std::atomic<long long> g_launches;
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+
+struct GemmDev {
+  CUtensorMap tmA;
+  CUtensorMap tmB;
+  int tiles_n, tiles_per_batch, tiles_m, num_tiles;
+  int a_rows, n, groups;
+  int a_gcs, b_grs, out_gcs;
+  int dil[NS2_GEMM_MAX_GROUPS];
+  int num_segs;
+  ns2_gemm_seg segs[NS2_GEMM_MAX_SEGS];
+  const float* bias;
+  int bias1_off;
+  void* out;
+  long long out_rs;
+  const float* resid;
+  long long resid_rs;
+  const float* film;
+  long long film_bs;
+  int film_gs;
+};
+
+template <int BN, int NACC>
+struct GemmCfg {
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BN == 256) ? 4 : 6;
+  static constexpr int ACC_COLS = BN * NACC;  // TMEM columns per accumulation stage
+  static constexpr int TMEM_COLS = (2 * ACC_COLS > 256) ? 512 : 256;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+struct TileCoord {
+  int g, b, n0, n_tile;
+};
+
+__device__ __forceinline__ TileCoord decode_tile(const GemmDev& p, int tile) {
+  TileCoord t;
+  const int per_group = p.tiles_m * p.tiles_n;
+  t.g = tile / per_group;
+  const int r = tile - t.g * per_group;
+  const int m_tile = r / p.tiles_n;
+  t.n_tile = r - m_tile * p.tiles_n;
+  t.b = m_tile / p.tiles_per_batch;
+  t.n0 = (m_tile - t.b * p.tiles_per_batch) * BM;
+  return t;
+}
+
+template <int BN, int NACC, int EPI>
+__global__ void __launch_bounds__(256, 1) gemm_kernel(const __grid_constant__ GemmDev p) {
+  using Cfg = GemmCfg<BN, NACC>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint64_t* full_bar = bars;                       // [STAGES]
+  uint64_t* empty_bar = bars + Cfg::STAGES;        // [STAGES]
+  uint64_t* tfull_bar = bars + 2 * Cfg::STAGES;    // [2]
+  uint64_t* tempty_bar = bars + 2 * Cfg::STAGES + 2;  // [2]
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmA);
+    tma_prefetch_desc(&p.tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < Cfg::STAGES; ++i) {
+      mbar_init(smem_u32(&full_bar[i]), 1);
+      mbar_init(smem_u32(&empty_bar[i]), 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(&tfull_bar[i]), 1);
+      mbar_init(smem_u32(&tempty_bar[i]), 4);  // one arrive per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(smem_u32(tmem_holder), Cfg::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  if (warp == 0) {
+    // =============================== TMA producer ===============================
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const TileCoord t = decode_tile(p, tile);
+        const int dil = p.dil[t.g];
+        for (int s = 0; s < p.num_segs; ++s) {
+          const ns2_gemm_seg sg = p.segs[s];
+          const int row0 = t.n0 - sg.shift_units * dil;
+          const int a_c0 = t.g * p.a_gcs + sg.a_col_off;
+          const int b_r0 = t.g * p.b_grs + t.n_tile * BN;
+          const int kblocks = (sg.k_len + BK - 1) / BK;
+          for (int kb = 0; kb < kblocks; ++kb, ++it) {
+            const uint32_t stage = it % Cfg::STAGES;
+            const uint32_t phase = (it / Cfg::STAGES) & 1;
+            mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+            const uint32_t fb = smem_u32(&full_bar[stage]);
+            mbar_arrive_expect_tx(fb, Cfg::STAGE_BYTES);
+            uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+            tma_load_3d(smem_u32(sa), &p.tmA, fb, a_c0 + kb * BK, row0, t.b);
+            tma_load_2d(smem_u32(sa + Cfg::A_BYTES), &p.tmB, fb, sg.b_col_off + kb * BK, b_r0);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer =================================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_f16(BM, BN, /*bf16*/ 1, 0, 0);
+      uint32_t it = 0;
+      uint32_t ti = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++ti) {
+        const uint32_t as = ti & 1;
+        const uint32_t aphase = (ti >> 1) & 1;
+        mbar_wait(smem_u32(&tempty_bar[as]), aphase ^ 1);
+        tc_fence_after();
+        uint32_t started = 0;  // bit a set once accumulator a has received its first MMA
+        for (int s = 0; s < p.num_segs; ++s) {
+          const int acc = p.segs[s].acc;
+          const uint32_t d_tmem = tmem_base + as * Cfg::ACC_COLS + acc * BN;
+          const int kblocks = (p.segs[s].k_len + BK - 1) / BK;
+          for (int kb = 0; kb < kblocks; ++kb, ++it) {
+            const uint32_t stage = it % Cfg::STAGES;
+            const uint32_t phase = (it / Cfg::STAGES) & 1;
+            mbar_wait(smem_u32(&full_bar[stage]), phase);
+            tc_fence_after();
+            const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+            const uint64_t da = umma_desc_sw128(sa, 16, 1024);
+            const uint64_t db = umma_desc_sw128(sa + Cfg::A_BYTES, 16, 1024);
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k) {
+              // advancing 16 elements (32 bytes) along K inside the 128-byte swizzle atom
+              tc_mma_f16(d_tmem, da + 2 * k, db + 2 * k, idesc, ((started >> acc) & 1) | (k > 0));
+            }
+            started |= 1u << acc;
+            tc_commit(smem_u32(&empty_bar[stage]));  // frees the smem slot when these MMAs retire
+          }
+        }
+        tc_commit(smem_u32(&tfull_bar[as]));  // accumulators of this tile complete
+      }
+    }
+  } else if (warp >= 4) {
+    // =============================== epilogue ===================================
+    const int ew = warp - 4;  // == warp % 4: the TMEM lane quarter this warp may read
+    const int row = ew * 32 + lane;
+    uint32_t ti = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++ti) {
+      const TileCoord t = decode_tile(p, tile);
+      const uint32_t as = ti & 1;
+      const uint32_t aphase = (ti >> 1) & 1;
+      mbar_wait(smem_u32(&tfull_bar[as]), aphase);
+      tc_fence_after();
+      const int npos = t.n0 + row;
+      const bool row_ok = npos < p.a_rows;
+      const long long grow = static_cast<long long>(t.b) * p.a_rows + npos;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + as * Cfg::ACC_COLS;
+
+      if constexpr (EPI == NS2_EPI_BF16 || EPI == NS2_EPI_F32) {
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          const int col0 = t.n_tile * BN + c * 32;
+          if (col0 >= p.n) break;
+          uint32_t r[32];
+          tmem_ld32(taddr + c * 32, r);
+          tmem_ld_wait();
+          float v[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+          if (p.bias != nullptr) {
+            const float4* bp = reinterpret_cast<const float4*>(p.bias + t.g * p.b_grs + col0);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 b4 = __ldg(bp + i);
+              v[4 * i + 0] += b4.x;
+              v[4 * i + 1] += b4.y;
+              v[4 * i + 2] += b4.z;
+              v[4 * i + 3] += b4.w;
+            }
+          }
+          if (row_ok) {
+            if constexpr (EPI == NS2_EPI_BF16) {
+              __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + grow * p.out_rs +
+                                  t.g * p.out_gcs + col0;
+              uint4* o4 = reinterpret_cast<uint4*>(op);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                uint4 w;
+                w.x = pack_bf16x2(v[8 * i + 0], v[8 * i + 1]);
+                w.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
+                w.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]);
+                w.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
+                o4[i] = w;
+              }
+            } else {
+              if (p.resid != nullptr) {
+                const float4* rp = reinterpret_cast<const float4*>(p.resid + grow * p.resid_rs +
+                                                                   t.g * p.out_gcs + col0);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  const float4 r4 = __ldg(rp + i);
+                  v[4 * i + 0] += r4.x;
+                  v[4 * i + 1] += r4.y;
+                  v[4 * i + 2] += r4.z;
+                  v[4 * i + 3] += r4.w;
+                }
+              }
+              float4* o4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) +
+                                                     grow * p.out_rs + t.g * p.out_gcs + col0);
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                o4[i] = make_float4(v[4 * i + 0], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+            }
+          }
+        }
+      } else if constexpr (EPI == NS2_EPI_GEGLU) {
+        static_assert(EPI != NS2_EPI_GEGLU || BN == 256, "GEGLU tiles pair 128 value + 128 gate rows");
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          const int pcol0 = t.n_tile * BN + c * 32;  // packed (value) column
+          if (pcol0 >= p.n) break;
+          uint32_t rv[32], rg[32];
+          tmem_ld32(taddr + c * 32, rv);
+          tmem_ld32(taddr + 128 + c * 32, rg);
+          tmem_ld_wait();
+          const float* bv = p.bias + t.g * p.b_grs + pcol0;
+          const float* bg = bv + 128;
+          uint32_t packed[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float x0 = __uint_as_float(rv[2 * i]) + __ldg(bv + 2 * i);
+            const float x1 = __uint_as_float(rv[2 * i + 1]) + __ldg(bv + 2 * i + 1);
+            const float g0 = __uint_as_float(rg[2 * i]) + __ldg(bg + 2 * i);
+            const float g1 = __uint_as_float(rg[2 * i + 1]) + __ldg(bg + 2 * i + 1);
+            packed[i] = pack_bf16x2(gelu_erf(g0) * x0, gelu_erf(g1) * x1);
+          }
+          if (row_ok) {
+            const int ocol0 = t.n_tile * 128 + c * 32;
+            uint4* o4 = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) +
+                                                 grow * p.out_rs + t.g * p.out_gcs + ocol0);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              o4[i] = make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2],
+                                 packed[4 * i + 3]);
+          }
+        }
+      } else {  // NS2_EPI_WAVENET
+        static_assert(EPI != NS2_EPI_WAVENET || NACC == 2, "wavenet block needs conv + res accumulators");
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          const int col0 = t.n_tile * BN + c * 32;
+          if (col0 >= p.n) break;
+          uint32_t rc[32], rr[32];
+          tmem_ld32(taddr + c * 32, rc);
+          tmem_ld32(taddr + BN + c * 32, rr);
+          tmem_ld_wait();
+          const float* b0 = p.bias + t.g * p.b_grs + col0;
+          const float* b1 = b0 + p.bias1_off;
+          const float* gm = p.film + t.b * p.film_bs + t.g * p.film_gs + col0;
+          const float* bt = gm + p.n;
+          uint32_t packed[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            float o[2];
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+              const int e = 2 * i + j;
+              float y = __uint_as_float(rc[e]) + __ldg(b0 + e);
+              y = y * __ldg(gm + e) + __ldg(bt + e);
+              const float gated = tanhf(y) * sigmoid_f(y);
+              o[j] = gated + __uint_as_float(rr[e]) + __ldg(b1 + e);
+            }
+            packed[i] = pack_bf16x2(o[0], o[1]);
+          }
+          if (row_ok) {
+            uint4* o4 = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) +
+                                                 grow * p.out_rs + t.g * p.out_gcs + col0);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              o4[i] = make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2],
+                                 packed[4 * i + 3]);
+          }
+        }
+      }
+      // release this accumulator stage back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[as]));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+template <int BN, int NACC, int EPI>
+static int launch_gemm(const GemmDev& dev, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN, NACC>;
+  static bool configured = false;
+  auto kern = gemm_kernel<BN, NACC, EPI>;
+  if (!configured) {
+    NS2_CUDA_CHECK(
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    configured = true;
+  }
+  const int grid = dev.num_tiles < num_sms() ? dev.num_tiles : num_sms();
+  kern<<<grid, 256, Cfg::SMEM_BYTES, stream>>>(dev);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  NS2_CUDA_CHECK(cudaGetLastError());
+  return kOk;
+}
+
+}  // namespace ns2
+
+extern "C" int ns2_gemm(const ns2_gemm_args* a, ns2_stream_t stream_) {
+  using namespace ns2;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  NS2_REQUIRE(a != nullptr, "ns2_gemm: args is NULL");
+  NS2_REQUIRE(a->A && a->B && a->out, "ns2_gemm: A, B and out must be non-NULL");
+  NS2_REQUIRE(a->groups >= 1 && a->groups <= NS2_GEMM_MAX_GROUPS, "ns2_gemm: groups=%d out of range",
+              a->groups);
+  NS2_REQUIRE(a->num_segs >= 1 && a->num_segs <= NS2_GEMM_MAX_SEGS, "ns2_gemm: num_segs=%d",
+              a->num_segs);
+  NS2_REQUIRE(a->n > 0 && a->n % 32 == 0, "ns2_gemm: n=%d must be a positive multiple of 32", a->n);
+  NS2_REQUIRE(a->a_rows > 0 && a->a_batches > 0, "ns2_gemm: empty A");
+  NS2_REQUIRE(a->a_row_stride % 8 == 0 && a->a_batch_stride % 8 == 0 && a->b_row_stride % 8 == 0,
+              "ns2_gemm: strides must be multiples of 8 elements (16 bytes)");
+  for (int s = 0; s < a->num_segs; ++s) {
+    const ns2_gemm_seg& sg = a->segs[s];
+    NS2_REQUIRE(sg.k_len > 0 && sg.acc >= 0 && sg.acc <= 1 && sg.shift_units >= 0,
+                "ns2_gemm: bad segment %d", s);
+    const bool ends_at_edge = (sg.b_col_off + sg.k_len == a->b_cols) &&
+                              ((a->groups - 1) * a->a_group_col_stride + sg.a_col_off + sg.k_len ==
+                               a->a_cols) &&
+                              a->groups == 1;
+    NS2_REQUIRE(sg.k_len % BK == 0 || ends_at_edge,
+                "ns2_gemm: segment %d k_len=%d is not a multiple of 64 and does not end at the edge", s,
+                sg.k_len);
+    NS2_REQUIRE(sg.acc == 0 || a->epilogue == NS2_EPI_WAVENET,
+                "ns2_gemm: second accumulator only exists for the WAVENET epilogue");
+  }
+  if (a->epilogue == NS2_EPI_WAVENET)
+    NS2_REQUIRE(a->film != nullptr && a->bias != nullptr, "ns2_gemm: WAVENET needs film and bias");
+  if (a->epilogue == NS2_EPI_GEGLU)
+    NS2_REQUIRE(a->bias != nullptr && a->n % 256 == 0,
+                "ns2_gemm: GEGLU needs bias and n %% 256 == 0 (n=%d)", a->n);
+  if (a->bias != nullptr)
+    NS2_REQUIRE(a->b_group_row_stride % 4 == 0 && a->bias1_off % 4 == 0 &&
+                    (reinterpret_cast<uintptr_t>(a->bias) & 15) == 0,
+                "ns2_gemm: bias must be 16-byte aligned with group strides multiple of 4");
+  NS2_REQUIRE(a->out_row_stride % 8 == 0 && a->out_group_col_stride % 8 == 0 &&
+                  (reinterpret_cast<uintptr_t>(a->out) & 15) == 0,
+              "ns2_gemm: out must be 16-byte aligned with strides multiple of 8");
+
+  GemmDev dev;
+  memset(&dev, 0, sizeof(dev));
+  {
+    const uint64_t dims[3] = {(uint64_t)a->a_cols, (uint64_t)a->a_rows, (uint64_t)a->a_batches};
+    const uint64_t strides[3] = {2, (uint64_t)a->a_row_stride * 2, (uint64_t)a->a_batch_stride * 2};
+    const uint32_t box[3] = {BK, BM, 1};
+    int rc = make_tmap_16bit(&dev.tmA, a->A, 3, dims, strides, box);
+    if (rc != kOk) return rc;
+  }
+  const int bn = (a->epilogue == NS2_EPI_WAVENET) ? 128
+                 : (a->epilogue == NS2_EPI_GEGLU) ? 256
+                 : (a->n % 256 == 0 && a->n >= 1024) ? 256
+                                                     : 128;
+  {
+    const uint64_t dims[2] = {(uint64_t)a->b_cols, (uint64_t)a->b_rows};
+    const uint64_t strides[2] = {2, (uint64_t)a->b_row_stride * 2};
+    const uint32_t box[2] = {BK, (uint32_t)bn};
+    int rc = make_tmap_16bit(&dev.tmB, a->B, 2, dims, strides, box);
+    if (rc != kOk) return rc;
+  }
+  dev.tiles_n = (a->n + bn - 1) / bn;
+  dev.tiles_per_batch = (a->a_rows + BM - 1) / BM;
+  dev.tiles_m = dev.tiles_per_batch * a->a_batches;
+  dev.num_tiles = dev.tiles_m * dev.tiles_n * a->groups;
+  dev.a_rows = a->a_rows;
+  dev.n = a->n;
+  dev.groups = a->groups;
+  dev.a_gcs = a->a_group_col_stride;
+  dev.b_grs = a->b_group_row_stride;
+  dev.out_gcs = a->out_group_col_stride;
+  for (int g = 0; g < NS2_GEMM_MAX_GROUPS; ++g) dev.dil[g] = a->dil[g];
+  dev.num_segs = a->num_segs;
+  for (int s = 0; s < a->num_segs; ++s) dev.segs[s] = a->segs[s];
+  dev.bias = a->bias;
+  dev.bias1_off = a->bias1_off;
+  dev.out = a->out;
+  dev.out_rs = a->out_row_stride;
+  dev.resid = a->resid;
+  dev.resid_rs = a->resid_row_stride;
+  dev.film = a->film;
+  dev.film_bs = a->film_batch_stride;
+  dev.film_gs = a->film_group_stride;
+
+  switch (a->epilogue) {
+    case NS2_EPI_BF16:
+      return bn == 256 ? launch_gemm<256, 1, NS2_EPI_BF16>(dev, stream)
+                       : launch_gemm<128, 1, NS2_EPI_BF16>(dev, stream);
+    case NS2_EPI_F32:
+      return bn == 256 ? launch_gemm<256, 1, NS2_EPI_F32>(dev, stream)
+                       : launch_gemm<128, 1, NS2_EPI_F32>(dev, stream);
+    case NS2_EPI_GEGLU:
+      return launch_gemm<256, 1, NS2_EPI_GEGLU>(dev, stream);
+    case NS2_EPI_WAVENET:
+      return launch_gemm<128, 2, NS2_EPI_WAVENET>(dev, stream);
+    default:
+      return set_error(kErrInvalidArg, "ns2_gemm: unknown epilogue %d", a->epilogue);
+  }
+}

@@ -1,0 +1,319 @@
+"""torch-tensor front end of the C ABI (include/ns2_b200.h).
+
+Every function takes CUDA tensors, validates what the kernels assume (dtype, contiguity of the channel
+dimension, alignment) and enqueues ONE library call on the current torch CUDA stream.  Nothing here computes
+on the host or falls back to PyTorch math: if the library is missing, `_lib.load()` raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import (AttnArgs, GemmArgs, NS2_EPI_BF16, NS2_EPI_F32, NS2_EPI_GEGLU, NS2_EPI_WAVENET,
+                   NS2_MSE_SCRATCH_PER_SAMPLE, check)
+
+EPI_BF16, EPI_F32, EPI_GEGLU, EPI_WAVENET = NS2_EPI_BF16, NS2_EPI_F32, NS2_EPI_GEGLU, NS2_EPI_WAVENET
+
+Seg = Tuple[int, int, int, int, int]  # (a_col_off, b_col_off, k_len, shift_units, acc)
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _req(t: torch.Tensor, dtype: torch.dtype, name: str) -> None:
+    if not t.is_cuda:
+        raise ValueError(f"{name} must be a CUDA tensor (the ns2_b200 ops have no CPU path)")
+    if t.dtype != dtype:
+        raise ValueError(f"{name} must be {dtype}, got {t.dtype}")
+    if t.dim() > 0 and t.stride(-1) != 1:
+        raise ValueError(f"{name} must be contiguous in its last dimension")
+
+
+def launch_count() -> int:
+    return int(_lib.load().ns2_launch_count())
+
+
+# --------------------------------------------------------------------------------------------------
+# GEMM family
+# --------------------------------------------------------------------------------------------------
+def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, n: int, epilogue: int,
+         segs: Optional[Sequence[Seg]] = None, bias: Optional[torch.Tensor] = None,
+         resid: Optional[torch.Tensor] = None, film: Optional[torch.Tensor] = None,
+         film_group_stride: int = 0, bias1_off: int = 0, groups: int = 1,
+         a_group_col_stride: int = 0, b_group_row_stride: int = 0, out_group_col_stride: int = 0,
+         dil: Optional[Sequence[int]] = None) -> torch.Tensor:
+    """out = epilogue(segmented_gemm(a, w)).  `a`: (batches, rows, cols) bf16 (may be a strided view),
+    `w`: packed bf16 weight (rows, K).  See include/ns2_b200.h section 1 for the exact semantics."""
+    lib = _lib.load()
+    _req(a, torch.bfloat16, "a")
+    _req(w, torch.bfloat16, "w")
+    if a.dim() != 3 or w.dim() != 2:
+        raise ValueError("a must be (batches, rows, cols) and w (rows, K)")
+    out_dtype = torch.float32 if epilogue == EPI_F32 else torch.bfloat16
+    _req(out, out_dtype, "out")
+    if out.dim() != 3 or out.shape[0] != a.shape[0] or out.shape[1] != a.shape[1]:
+        raise ValueError(f"out must be (batches, rows, *), got {tuple(out.shape)} for a {tuple(a.shape)}")
+    if out.stride(0) != out.shape[1] * out.stride(1):
+        raise ValueError("out rows must be uniformly strided across batches")
+    if segs is None:
+        segs = [(0, 0, a.shape[2], 0, 0)]
+    args = GemmArgs()
+    args.A = a.data_ptr()
+    args.a_row_stride, args.a_batch_stride = a.stride(1), a.stride(0)
+    args.a_batches, args.a_rows, args.a_cols = a.shape
+    args.B = w.data_ptr()
+    args.b_row_stride = w.stride(0)
+    args.b_rows, args.b_cols = w.shape
+    args.n = n
+    args.groups = groups
+    args.a_group_col_stride = a_group_col_stride
+    args.b_group_row_stride = b_group_row_stride
+    args.out_group_col_stride = out_group_col_stride
+    for g in range(_lib.NS2_GEMM_MAX_GROUPS):
+        args.dil[g] = int(dil[g]) if dil is not None and g < len(dil) else 1
+    args.num_segs = len(segs)
+    for i, s in enumerate(segs):
+        sg = args.segs[i]
+        sg.a_col_off, sg.b_col_off, sg.k_len, sg.shift_units, sg.acc = (int(v) for v in s)
+    args.epilogue = epilogue
+    if bias is not None:
+        _req(bias, torch.float32, "bias")
+    args.bias = _ptr(bias)
+    args.bias1_off = bias1_off
+    args.out = out.data_ptr()
+    args.out_row_stride = out.stride(1)
+    if resid is not None:
+        _req(resid, torch.float32, "resid")
+        if resid.shape != out.shape or resid.stride(0) != resid.shape[1] * resid.stride(1):
+            raise ValueError("resid must match out's shape with uniformly strided rows")
+        args.resid_row_stride = resid.stride(1)
+    args.resid = _ptr(resid)
+    if film is not None:
+        _req(film, torch.float32, "film")
+        args.film_batch_stride = film.stride(0)
+    args.film = _ptr(film)
+    args.film_group_stride = film_group_stride
+    check(lib.ns2_gemm(C.byref(args), _stream()), "ns2_gemm")
+    return out
+
+
+def conv3_segs(k_len: int, tap_stride: Optional[int] = None, acc: int = 0, a_col_off: int = 0,
+               b_col_off: int = 0) -> list:
+    """Segments of a causal k=3 conv whose packed weight holds tap t at columns [t*tap_stride, +k_len):
+    tap t multiplies x[n - (2 - t) * dilation]   (CausalConv1d, ns2.py:583-595)."""
+    ts = k_len if tap_stride is None else tap_stride
+    return [(a_col_off, b_col_off + t * ts, k_len, 2 - t, acc) for t in range(3)]
+
+
+# --------------------------------------------------------------------------------------------------
+# attention
+# --------------------------------------------------------------------------------------------------
+def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tensor, *, heads: int,
+              scale: Optional[float] = None) -> torch.Tensor:
+    """q: (B, Nq, heads*64), k/v: (B, Nk, heads*64) bf16 (strided views into a fused projection are fine)."""
+    lib = _lib.load()
+    for name, t in (("q", q), ("k", k), ("v", v), ("out", out)):
+        _req(t, torch.bfloat16, name)
+        if t.dim() != 3 or t.shape[2] != heads * 64:
+            raise ValueError(f"{name} must be (B, N, heads*64), got {tuple(t.shape)}")
+    args = AttnArgs()
+    args.q, args.q_row_stride, args.q_batch_stride = q.data_ptr(), q.stride(1), q.stride(0)
+    args.k, args.k_row_stride, args.k_batch_stride = k.data_ptr(), k.stride(1), k.stride(0)
+    args.v, args.v_row_stride, args.v_batch_stride = v.data_ptr(), v.stride(1), v.stride(0)
+    args.out, args.o_row_stride, args.o_batch_stride = out.data_ptr(), out.stride(1), out.stride(0)
+    args.batches, args.heads = q.shape[0], heads
+    args.q_len, args.kv_len, args.dim_head = q.shape[1], k.shape[1], 64
+    args.scale = float(scale if scale is not None else 64 ** -0.5)
+    check(lib.ns2_attn_fwd(C.byref(args), _stream()), "ns2_attn_fwd")
+    return out
+
+
+# --------------------------------------------------------------------------------------------------
+# norms, small layers, casts
+# --------------------------------------------------------------------------------------------------
+def rmsnorm_film(x: torch.Tensor, out: torch.Tensor, *, gamma: Optional[torch.Tensor] = None,
+                 film: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x: (B, N, D) f32 -> out (B, N, D) bf16.  film: (B, >=2D) f32 view whose row b holds [gamma_b | beta_b]."""
+    lib = _lib.load()
+    _req(x, torch.float32, "x")
+    _req(out, torch.bfloat16, "out")
+    if not (x.is_contiguous() and out.is_contiguous()):
+        raise ValueError("x and out must be contiguous")
+    B, N, D = x.shape
+    if gamma is not None:
+        _req(gamma, torch.float32, "gamma")
+    film_bs = 0
+    if film is not None:
+        _req(film, torch.float32, "film")
+        film_bs = film.stride(0)
+    check(lib.ns2_rmsnorm_film(x.data_ptr(), D, B * N, D, N, _ptr(gamma), _ptr(film), film_bs,
+                               out.data_ptr(), D, _stream()), "ns2_rmsnorm_film")
+    return out
+
+
+def rmsnorm_f32(x: torch.Tensor, out: torch.Tensor, gamma: Optional[torch.Tensor]) -> torch.Tensor:
+    lib = _lib.load()
+    _req(x, torch.float32, "x")
+    _req(out, torch.float32, "out")
+    D = x.shape[-1]
+    rows = x.numel() // D
+    check(lib.ns2_rmsnorm_f32(x.data_ptr(), D, rows, D, _ptr(gamma), out.data_ptr(), D, _stream()),
+          "ns2_rmsnorm_f32")
+    return out
+
+
+def time_cond(times: torch.Tensor, freqs: torch.Tensor, w: torch.Tensor, bias: torch.Tensor,
+              out: torch.Tensor) -> torch.Tensor:
+    """out[b] = silu(W @ [t_b, sin(2 pi t_b f), cos(2 pi t_b f)] + bias); out may be a column slice."""
+    lib = _lib.load()
+    for name, t in (("times", times), ("freqs", freqs), ("w", w), ("bias", bias), ("out", out)):
+        _req(t, torch.float32, name)
+    check(lib.ns2_time_cond(times.data_ptr(), times.shape[0], freqs.data_ptr(), freqs.shape[0],
+                            w.data_ptr(), bias.data_ptr(), w.shape[0], out.data_ptr(), out.stride(0),
+                            _stream()), "ns2_time_cond")
+    return out
+
+
+def small_linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], out: torch.Tensor,
+                 act: int = 0) -> torch.Tensor:
+    lib = _lib.load()
+    for name, t in (("x", x), ("w", w), ("out", out)):
+        _req(t, torch.float32, name)
+    check(lib.ns2_small_linear(x.data_ptr(), x.stride(0), x.shape[0], x.shape[1], w.data_ptr(),
+                               _ptr(bias), w.shape[0], act, out.data_ptr(), out.stride(0), _stream()),
+          "ns2_small_linear")
+    return out
+
+
+def cast_bf16(x: torch.Tensor, out: torch.Tensor, add: Optional[torch.Tensor] = None) -> torch.Tensor:
+    lib = _lib.load()
+    _req(x, torch.float32, "x")
+    _req(out, torch.bfloat16, "out")
+    if not (x.is_contiguous() and out.is_contiguous()) or x.numel() != out.numel():
+        raise ValueError("cast_bf16 needs contiguous tensors of equal size")
+    if add is not None:
+        _req(add, torch.float32, "add")
+        if not add.is_contiguous() or add.numel() != x.numel():
+            raise ValueError("add must be contiguous and the same size as x")
+    check(lib.ns2_cast_bf16(x.data_ptr(), _ptr(add), x.numel(), out.data_ptr(), _stream()),
+          "ns2_cast_bf16")
+    return out
+
+
+def mean_rows(x: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+    lib = _lib.load()
+    _req(x, torch.float32, "x")
+    _req(out, torch.float32, "out")
+    B, N, D = x.shape
+    check(lib.ns2_mean_rows(x.contiguous().data_ptr(), B, N, D, out.data_ptr(), _stream()),
+          "ns2_mean_rows")
+    return out
+
+
+def transpose_cast(x: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+    """(B, C, L) f32 channel-first -> (B, L, C) bf16."""
+    lib = _lib.load()
+    _req(x, torch.float32, "x")
+    _req(out, torch.bfloat16, "out")
+    B, Cc, L = x.shape
+    check(lib.ns2_transpose_cast(x.contiguous().data_ptr(), B, Cc, L, out.data_ptr(), _stream()),
+          "ns2_transpose_cast")
+    return out
+
+
+# --------------------------------------------------------------------------------------------------
+# diffusion element-wise
+# --------------------------------------------------------------------------------------------------
+def q_sample(x0, noise, alpha, sigma, x_t, target=None):
+    lib = _lib.load()
+    B = x0.shape[0]
+    per = x0.numel() // B
+    for name, t in (("x0", x0), ("noise", noise), ("alpha", alpha), ("sigma", sigma), ("x_t", x_t)):
+        _req(t, torch.float32, name)
+    check(lib.ns2_q_sample(x0.data_ptr(), noise.data_ptr(), alpha.data_ptr(), sigma.data_ptr(), B, per,
+                           x_t.data_ptr(), _ptr(target), _stream()), "ns2_q_sample")
+    return x_t, target
+
+
+def mse_rows(pred, target, out, scratch=None):
+    lib = _lib.load()
+    B = pred.shape[0]
+    per = pred.numel() // B
+    if scratch is None:
+        scratch = torch.empty(B * NS2_MSE_SCRATCH_PER_SAMPLE, device=pred.device, dtype=torch.float32)
+    check(lib.ns2_mse_rows(pred.data_ptr(), target.data_ptr(), B, per, scratch.data_ptr(),
+                           out.data_ptr(), _stream()), "ns2_mse_rows")
+    return out
+
+
+def ddim_step(x, v, alpha, sigma, alpha_next, sigma_next):
+    lib = _lib.load()
+    B = x.shape[0]
+    per = x.numel() // B
+    check(lib.ns2_ddim_step(x.data_ptr(), v.data_ptr(), alpha.data_ptr(), sigma.data_ptr(),
+                            alpha_next.data_ptr(), sigma_next.data_ptr(), B, per, _stream()),
+          "ns2_ddim_step")
+    return x
+
+
+def cfg_combine(cond, null, scale, out):
+    lib = _lib.load()
+    check(lib.ns2_cfg_combine(cond.data_ptr(), null.data_ptr(), float(scale), cond.numel(),
+                              out.data_ptr(), _stream()), "ns2_cfg_combine")
+    return out
+
+
+# --------------------------------------------------------------------------------------------------
+# RVQ
+# --------------------------------------------------------------------------------------------------
+def rvq_prepare(codebooks: torch.Tensor):
+    """codebooks (Q, K, 128) f32 -> (fp16 copy, ||c||^2 (Q, K) f32, meta (Q, 2) f32)."""
+    lib = _lib.load()
+    _req(codebooks, torch.float32, "codebooks")
+    cb = codebooks.contiguous()
+    Q, K, D = cb.shape
+    cb16 = torch.empty((Q, K, D), device=cb.device, dtype=torch.float16)
+    cn2 = torch.empty((Q, K), device=cb.device, dtype=torch.float32)
+    meta = torch.empty((Q, 2), device=cb.device, dtype=torch.float32)
+    check(lib.ns2_rvq_prepare(cb.data_ptr(), Q, K, D, cb16.data_ptr(), cn2.data_ptr(), meta.data_ptr(),
+                              _stream()), "ns2_rvq_prepare")
+    return cb16, cn2, meta
+
+
+def rvq_encode(frames: torch.Tensor, codebooks: torch.Tensor, prepared, codes: Optional[torch.Tensor] = None,
+               stats: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """frames (F, 128) f32 -> codes (F, Q) int64."""
+    lib = _lib.load()
+    _req(frames, torch.float32, "frames")
+    cb16, cn2, meta = prepared
+    cb = codebooks.contiguous()
+    Q, K, D = cb.shape
+    fr = frames.contiguous()
+    F = fr.shape[0]
+    if codes is None:
+        codes = torch.empty((F, Q), device=fr.device, dtype=torch.int64)
+    check(lib.ns2_rvq_encode(fr.data_ptr(), F, D, cb.data_ptr(), cb16.data_ptr(), cn2.data_ptr(),
+                             meta.data_ptr(), Q, K, codes.data_ptr(), _ptr(stats), _stream()),
+          "ns2_rvq_encode")
+    return codes
+
+
+def rvq_decode(codes: torch.Tensor, codebooks: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    lib = _lib.load()
+    cb = codebooks.contiguous()
+    Q, K, D = cb.shape
+    cd = codes.contiguous()
+    F = cd.shape[0]
+    if out is None:
+        out = torch.empty((F, D), device=cb.device, dtype=torch.float32)
+    check(lib.ns2_rvq_decode(cd.data_ptr(), F, Q, K, D, cb.data_ptr(), out.data_ptr(), _stream()),
+          "ns2_rvq_decode")
+    return out
