@@ -1,0 +1,536 @@
+"""`Model`: the NaturalSpeech2 denoiser (time FiLM -> Wavenet -> conditionable Transformer) on sm_100a kernels.
+
+Drop-in for `naturalspeech2_pytorch.Model` (ns2.py:811-1000): same constructor, same `forward` /
+`forward_with_cond_scale` signatures, same parameter names and shapes, so a reference
+state_dict loads unchanged.  The module tree below only *holds* parameters (nn.Linear / nn.Conv1d instances are
+never called); the math runs through `ops` (libns2b200.so):
+
+  time embedding     ops.time_cond                         ns2.py:108-120, 839-843
+  all FiLM vectors   one stacked GEMM for the 32 wavenet blocks + every adaptive RMSNorm   ns2.py:613,731
+  Wavenet            init conv, 4 launches of 8 dilation columns each (conv + res_conv + FiLM + gate fused),
+                     skip sum as one K=8*dim GEMM, final conv                              ns2.py:597-725
+  Transformer layer  RMSNorm+FiLM -> fused QKV GEMM -> flash attention -> out-proj(+residual)
+                     [-> cross attention over the perceiver latents]
+                     -> RMSNorm+FiLM -> GEGLU GEMM -> causal k=3 conv GEMM -> out GEMM(+residual)   ns2.py:786-809
+Numerics: bf16 tensor-core operands, fp32 accumulation, fp32 residual stream / norm statistics / softmax,
+fp32 output (the protocol of SURVEY section 7, H1).
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Optional
+
+import torch
+from torch import nn
+
+from . import ops
+
+_KBLK = 64
+
+
+def _exists(v):
+    return v is not None
+
+
+def _round_up(v: int, m: int) -> int:
+    return (v + m - 1) // m * m
+
+
+class _NoParam(nn.Module):
+    """Placeholder keeping Sequential indices aligned with the reference (Reduce / Rearrange / GEGLU / SiLU)."""
+
+
+class _SinusoidalFreqs(nn.Module):
+    """Parameter holder of LearnedSinusoidalPosEmb (ns2.py:108-120): `weights` (dim/2,)."""
+
+    def __init__(self, dim: int):
+        super().__init__()
+        assert dim % 2 == 0
+        self.weights = nn.Parameter(torch.randn(dim // 2))
+
+
+class _AttentionParams(nn.Module):
+    """Parameter holder of Attention (ns2.py:1029-1053): to_q, to_kv, to_out, all bias-free."""
+
+    def __init__(self, dim: int, dim_head: int, heads: int):
+        super().__init__()
+        inner = dim_head * heads
+        self.to_q = nn.Linear(dim, inner, bias=False)
+        self.to_kv = nn.Linear(dim, inner * 2, bias=False)
+        self.to_out = nn.Linear(inner, dim, bias=False)
+
+
+class _RMSNormParams(nn.Module):
+    """Parameter holder of RMSNorm (ns2.py:727-734)."""
+
+    def __init__(self, dim: int, scale: bool = True, dim_cond: Optional[int] = None):
+        super().__init__()
+        self.to_gamma_beta = nn.Linear(dim_cond, dim * 2) if _exists(dim_cond) else None
+        self.gamma = nn.Parameter(torch.ones(dim)) if scale else None
+
+
+def _feedforward_params(dim: int, mult: int, causal_conv: bool) -> nn.Sequential:
+    """Same Sequential indices (and RNG order: conv first) as FeedForward (ns2.py:1009-1025)."""
+    inner = int(dim * mult * 2 / 3)
+    conv = None
+    if causal_conv:
+        conv = nn.Sequential(_NoParam(), nn.Conv1d(inner, inner, 3), _NoParam())
+    mods = [nn.Linear(dim, inner * 2), _NoParam()]
+    if conv is not None:
+        mods.append(conv)
+    mods.append(nn.Linear(inner, dim))
+    return nn.Sequential(*mods)
+
+
+class _WavenetBlockParams(nn.Module):
+    def __init__(self, dim: int, dilation: int, skip_conv: bool, dim_cond_mult: int):
+        super().__init__()
+        self.to_time_cond = nn.Linear(dim * dim_cond_mult, dim * 2)
+        self.conv = nn.Conv1d(dim, dim, 3, dilation=dilation)
+        self.res_conv = nn.Conv1d(dim, dim, 1)
+        self.skip_conv = nn.Conv1d(dim, dim, 1) if skip_conv else None
+
+
+class _WavenetStackParams(nn.Module):
+    def __init__(self, dim: int, layers: int, has_skip: bool, dim_cond_mult: int):
+        super().__init__()
+        self.has_skip = has_skip
+        self.blocks = nn.ModuleList([
+            _WavenetBlockParams(dim, 2 ** i, has_skip, dim_cond_mult) for i in range(layers)])
+
+
+class _WavenetParams(nn.Module):
+    def __init__(self, dim: int, stacks: int, layers: int, dim_cond_mult: int):
+        super().__init__()
+        self.init_conv = nn.Conv1d(dim, dim, 3)
+        self.stacks = nn.ModuleList([
+            _WavenetStackParams(dim, layers, s == stacks - 1, dim_cond_mult) for s in range(stacks)])
+        self.final_conv = nn.Conv1d(dim, dim, 1)
+
+
+class _TransformerParams(nn.Module):
+    def __init__(self, dim, depth, dim_head, heads, ff_mult, dim_cond_mult, cross_attn):
+        super().__init__()
+        dim_cond = dim * dim_cond_mult
+        self.layers = nn.ModuleList([])
+        for _ in range(depth):
+            self.layers.append(nn.ModuleList([
+                _RMSNormParams(dim, scale=False, dim_cond=dim_cond),
+                _AttentionParams(dim, dim_head, heads),
+                _RMSNormParams(dim, scale=False, dim_cond=dim_cond) if cross_attn else None,
+                _AttentionParams(dim, dim_head, heads) if cross_attn else None,
+                _RMSNormParams(dim, scale=False, dim_cond=dim_cond),
+                _feedforward_params(dim, ff_mult, causal_conv=True),
+            ]))
+        self.to_pred = nn.Sequential(_RMSNormParams(dim), nn.Linear(dim, dim, bias=False))
+
+
+class _PerceiverParams(nn.Module):
+    def __init__(self, dim, depth, dim_context, num_latents, dim_head, heads, ff_mult=4):
+        super().__init__()
+        self.proj_context = nn.Linear(dim_context, dim) if dim_context != dim else nn.Identity()
+        self.latents = nn.Parameter(torch.randn(num_latents, dim))
+        nn.init.normal_(self.latents, std=0.02)
+        self.layers = nn.ModuleList([
+            nn.ModuleList([_AttentionParams(dim, dim_head, heads), _feedforward_params(dim, ff_mult, False)])
+            for _ in range(depth)])
+        self.norm = _RMSNormParams(dim)
+
+
+def _prob_mask_like(shape, prob, device):
+    # ns2.py:79-85 — kept in torch so the RNG stream matches the reference
+    if prob == 1:
+        return torch.ones(shape, device=device, dtype=torch.bool)
+    if prob == 0:
+        return torch.zeros(shape, device=device, dtype=torch.bool)
+    return torch.zeros(shape, device=device).float().uniform_(0, 1) < prob
+
+
+class Model(nn.Module):
+    """B200 denoiser; constructor and call signatures of ns2.py:811-937."""
+
+    def __init__(self, dim, *, depth, dim_head=64, heads=8, ff_mult=4, wavenet_layers=8,
+                 wavenet_stacks=4, dim_cond_mult=4, use_flash_attn=True, dim_prompt=None,
+                 num_latents_m=32, resampler_depth=2, cond_drop_prob=0., condition_on_prompt=False):
+        super().__init__()
+        if dim_head != 64:
+            raise NotImplementedError("the sm_100a attention kernel is specialised for dim_head=64")
+        if dim % 128 != 0 or dim > 1024:
+            raise NotImplementedError("dim must be a multiple of 128 (<= 1024) for the sm_100a kernels")
+        if not 1 <= wavenet_layers <= 8:
+            raise NotImplementedError("wavenet_layers must be in [1, 8] (one launch covers <= 8 dilation columns)")
+        self.dim = dim
+        self.depth = depth
+        self.heads = heads
+        self.dim_head = dim_head
+        self.inner = heads * dim_head
+        self.ff_inner = int(dim * ff_mult * 2 / 3)
+        self.wavenet_layers = wavenet_layers
+        self.wavenet_stacks = wavenet_stacks
+        self.num_latents_m = num_latents_m
+        self.dim_prompt = dim_prompt
+        self.use_flash_attn = use_flash_attn  # accepted for signature parity; the flash kernel is the only path
+
+        dim_time = dim * dim_cond_mult
+        self.dim_time = dim_time
+        self.to_time_cond = nn.Sequential(_SinusoidalFreqs(dim), nn.Linear(dim + 1, dim_time), _NoParam())
+
+        self.cond_drop_prob = cond_drop_prob
+        self.condition_on_prompt = condition_on_prompt
+        self.to_prompt_cond = None
+        if condition_on_prompt:
+            assert _exists(dim_prompt), "dim_prompt is required when condition_on_prompt=True"
+            if dim_prompt % _KBLK != 0:
+                raise NotImplementedError("dim_prompt must be a multiple of 64")
+            self.null_prompt_cond = nn.Parameter(torch.randn(dim_time))
+            self.null_prompt_tokens = nn.Parameter(torch.randn(num_latents_m, dim))
+            nn.init.normal_(self.null_prompt_cond, std=0.02)
+            nn.init.normal_(self.null_prompt_tokens, std=0.02)
+            self.to_prompt_cond = nn.Sequential(_NoParam(), nn.Linear(dim_prompt, dim_time), _NoParam())
+            self.perceiver_resampler = _PerceiverParams(dim, resampler_depth, dim_prompt, num_latents_m,
+                                                        dim_head, heads)
+        self.null_cond = None
+        self.cond_to_model_dim = None
+        if condition_on_prompt:
+            self.cond_to_model_dim = nn.Conv1d(dim_prompt, dim, 1)
+            self.null_cond = nn.Parameter(torch.zeros(dim, 1))
+
+        dim_cond_mult = dim_cond_mult * (2 if condition_on_prompt else 1)
+        self.dim_cond = dim * dim_cond_mult
+        self.wavenet = _WavenetParams(dim, wavenet_stacks, wavenet_layers, dim_cond_mult)
+        self.transformer = _TransformerParams(dim, depth, dim_head, heads, ff_mult, dim_cond_mult,
+                                              cross_attn=condition_on_prompt)
+        self._packed: Optional[Dict[str, torch.Tensor]] = None
+        self._packed_sig = None
+        self._ws: Dict[tuple, Dict[str, torch.Tensor]] = {}
+        self.freeze_packed = False  # set True to skip the per-call parameter-version check (inference loops)
+
+    @property
+    def device(self):
+        return next(self.parameters()).device
+
+    # ----------------------------------------------------------------------------------------------
+    # weight packing: fp32 parameters -> bf16 tensor-core layouts (rebuilt whenever a parameter changes)
+    # ----------------------------------------------------------------------------------------------
+    def _signature(self):
+        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+
+    def packed(self) -> Dict[str, torch.Tensor]:
+        if self._packed is not None and self.freeze_packed:
+            return self._packed
+        sig = self._signature()
+        if self._packed is None or sig != self._packed_sig:
+            with torch.no_grad():
+                self._packed = self._pack()
+            self._packed_sig = sig
+        return self._packed
+
+    @staticmethod
+    def _bf(t):
+        return t.detach().to(torch.bfloat16).contiguous()
+
+    @staticmethod
+    def _conv3_pack(w, k_pad=None, o_pad=None):
+        """(O, I, 3) -> (O_pad, 3*I_pad) with tap t at columns [t*I_pad, t*I_pad + I); zero padded."""
+        O, I, _ = w.shape
+        k_pad = k_pad or I
+        o_pad = o_pad or O
+        out = w.new_zeros(o_pad, 3 * k_pad)
+        for t in range(3):
+            out[:O, t * k_pad:t * k_pad + I] = w[:, :, t]
+        return out
+
+    def _pack_ff(self, ff: nn.Sequential, conv: bool) -> Dict[str, torch.Tensor]:
+        D, Di = self.dim, self.ff_inner
+        Dp = _round_up(Di, 128)
+        lin1, lin2 = ff[0], ff[-1]
+        dev = lin1.weight.device
+        wv = torch.zeros(Dp, D, device=dev)
+        wg = torch.zeros(Dp, D, device=dev)
+        wv[:Di], wg[:Di] = lin1.weight[:Di], lin1.weight[Di:]  # first half = value, second = gate (ns2.py:1006)
+        bv = torch.zeros(Dp, device=dev)
+        bg = torch.zeros(Dp, device=dev)
+        bv[:Di], bg[:Di] = lin1.bias[:Di], lin1.bias[Di:]
+        w1 = torch.stack((wv.view(-1, 128, D), wg.view(-1, 128, D)), dim=1).reshape(2 * Dp, D)
+        b1 = torch.stack((bv.view(-1, 128), bg.view(-1, 128)), dim=1).reshape(2 * Dp)
+        w2 = torch.zeros(D, Dp, device=dev)
+        w2[:, :Di] = lin2.weight
+        out = {"w1": self._bf(w1), "b1": b1.float().contiguous(), "w2": self._bf(w2),
+               "b2": lin2.bias.detach().float().contiguous()}
+        if conv:
+            c = ff[2][1]
+            out["wc"] = self._bf(self._conv3_pack(c.weight, k_pad=Dp, o_pad=Dp))
+            bc = torch.zeros(Dp, device=dev)
+            bc[:Di] = c.bias
+            out["bc"] = bc
+        return out
+
+    def _pack(self) -> Dict[str, torch.Tensor]:
+        D, G = self.dim, self.wavenet_layers
+        P: Dict[str, torch.Tensor] = {}
+        # ---- every FiLM projection as one stacked (rows, dim_cond) matrix ----
+        film_w, film_b = [], []
+        for st in self.wavenet.stacks:
+            for blk in st.blocks:
+                film_w.append(blk.to_time_cond.weight)
+                film_b.append(blk.to_time_cond.bias)
+        self._film_tr_off = len(film_w) * 2 * D
+        self._norms_per_layer = 3 if self.condition_on_prompt else 2
+        for layer in self.transformer.layers:
+            for idx in (0, 2, 4):
+                if layer[idx] is not None:
+                    film_w.append(layer[idx].to_gamma_beta.weight)
+                    film_b.append(layer[idx].to_gamma_beta.bias)
+        P["film_w"] = self._bf(torch.cat(film_w, dim=0))
+        P["film_b"] = torch.cat(film_b, dim=0).detach().float().contiguous()
+        # ---- wavenet ----
+        wn = self.wavenet
+        P["wn_init_w"] = self._bf(self._conv3_pack(wn.init_conv.weight))
+        P["wn_init_b"] = wn.init_conv.bias.detach().float().contiguous()
+        for s, st in enumerate(wn.stacks):
+            ws, bc, br = [], [], []
+            for blk in st.blocks:
+                ws.append(torch.cat((self._conv3_pack(blk.conv.weight), blk.res_conv.weight[:, :, 0]), dim=1))
+                bc.append(blk.conv.bias)
+                br.append(blk.res_conv.bias)
+            P[f"wn{s}_w"] = self._bf(torch.cat(ws, dim=0))                      # (G*D, 4*D)
+            P[f"wn{s}_b"] = torch.cat(bc + br).detach().float().contiguous()   # [conv biases | res biases]
+        last = wn.stacks[-1]
+        P["wn_skip_w"] = self._bf(torch.cat([b.skip_conv.weight[:, :, 0] for b in last.blocks], dim=1))
+        P["wn_skip_b"] = torch.stack([b.skip_conv.bias for b in last.blocks]).sum(0).detach().float().contiguous()
+        P["wn_final_w"] = self._bf(wn.final_conv.weight[:, :, 0])
+        P["wn_final_b"] = wn.final_conv.bias.detach().float().contiguous()
+        # ---- transformer ----
+        kv_all = []
+        for l, layer in enumerate(self.transformer.layers):
+            attn = layer[1]
+            P[f"l{l}_qkv"] = self._bf(torch.cat((attn.to_q.weight, attn.to_kv.weight), dim=0))
+            P[f"l{l}_o"] = self._bf(attn.to_out.weight)
+            if layer[3] is not None:
+                P[f"l{l}_xq"] = self._bf(layer[3].to_q.weight)
+                P[f"l{l}_xo"] = self._bf(layer[3].to_out.weight)
+                kv_all.append(layer[3].to_kv.weight)
+            for k, v in self._pack_ff(layer[5], conv=True).items():
+                P[f"l{l}_ff_{k}"] = v
+        if kv_all:
+            P["x_kv_all"] = self._bf(torch.cat(kv_all, dim=0))  # (depth*2*inner, D): cross K/V of all layers
+        P["pred_gamma"] = self.transformer.to_pred[0].gamma.detach().float().contiguous()
+        P["pred_w"] = self._bf(self.transformer.to_pred[1].weight)
+        # ---- conditioning ----
+        if self.condition_on_prompt:
+            pr = self.perceiver_resampler
+            if isinstance(pr.proj_context, nn.Linear):
+                P["pr_proj_w"] = self._bf(pr.proj_context.weight)
+                P["pr_proj_b"] = pr.proj_context.bias.detach().float().contiguous()
+            for i, (attn, ff) in enumerate(pr.layers):
+                P[f"pr{i}_q"] = self._bf(attn.to_q.weight)
+                P[f"pr{i}_kv"] = self._bf(attn.to_kv.weight)
+                P[f"pr{i}_o"] = self._bf(attn.to_out.weight)
+                for k, v in self._pack_ff(ff, conv=False).items():
+                    P[f"pr{i}_ff_{k}"] = v
+            P["cond_w"] = self._bf(self.cond_to_model_dim.weight[:, :, 0])
+            P["cond_b"] = self.cond_to_model_dim.bias.detach().float().contiguous()
+        return P
+
+    # ----------------------------------------------------------------------------------------------
+    # workspaces (stable addresses per problem shape so a forward can be captured in a CUDA graph)
+    # ----------------------------------------------------------------------------------------------
+    def _workspace(self, B: int, N: int, dev) -> Dict[str, torch.Tensor]:
+        key = (B, N, str(dev))
+        ws = self._ws.get(key)
+        if ws is not None:
+            return ws
+        D, G, inner = self.dim, self.wavenet_layers, self.inner
+        Dp = _round_up(self.ff_inner, 128)
+        bf, f32 = torch.bfloat16, torch.float32
+        e = lambda *s, dt=bf: torch.empty(*s, device=dev, dtype=dt)
+        ws = {
+            "t": e(B, self.dim_cond, dt=f32), "t_bf": e(1, B, self.dim_cond),
+            "film": e(1, B, self.packed()["film_w"].shape[0], dt=f32),
+            "x_bf": e(B, N, D), "h": e(B, N, D),
+            "wn_a": e(B, N, G * D), "wn_b": e(B, N, G * D),
+            "x_res": e(B, N, D, dt=f32),
+            "qkv": e(B, N, 3 * inner), "attn_o": e(B, N, inner),
+            "ff_g": e(B, N, Dp), "ff_c": e(B, N, Dp),
+            "out": e(B, N, D, dt=f32),
+        }
+        if self.condition_on_prompt:
+            M = self.num_latents_m
+            ws.update({"xq": e(B, N, inner), "c_bf": e(B, M, D),
+                       "xkv": e(B, M, self.depth * 2 * inner)})
+        self._ws[key] = ws
+        return ws
+
+    # ----------------------------------------------------------------------------------------------
+    # conditioning (timestep-invariant; cache across sampling steps via `precompute_conditioning`)
+    # ----------------------------------------------------------------------------------------------
+    def _perceiver(self, prompt: torch.Tensor) -> torch.Tensor:
+        """PerceiverResampler.forward (ns2.py:568-579) -> (B, M, D) fp32."""
+        P, D, M, inner, H = self.packed(), self.dim, self.num_latents_m, self.inner, self.heads
+        pr = self.perceiver_resampler
+        B, Np, _ = prompt.shape
+        dev = prompt.device
+        bf = torch.bfloat16
+        ctx_len = M + Np
+        cat = torch.empty(B, ctx_len, D, device=dev, dtype=bf)  # [latents ; projected prompt]
+        p_bf = ops.cast_bf16(prompt.contiguous().float(), torch.empty(B, Np, self.dim_prompt, device=dev, dtype=bf))
+        if "pr_proj_w" in P:
+            ops.gemm(p_bf, P["pr_proj_w"], cat[:, M:], n=D, epilogue=ops.EPI_BF16, bias=P["pr_proj_b"])
+        else:
+            cat[:, M:].copy_(p_bf)
+        lat = pr.latents.detach().float().unsqueeze(0).expand(B, M, D).contiguous()
+        lat_bf = torch.empty(B, M, D, device=dev, dtype=bf)
+        q = torch.empty(B, M, inner, device=dev, dtype=bf)
+        kv = torch.empty(B, ctx_len, 2 * inner, device=dev, dtype=bf)
+        o = torch.empty(B, M, inner, device=dev, dtype=bf)
+        Dp = _round_up(self.ff_inner, 128)
+        g = torch.empty(B, M, Dp, device=dev, dtype=bf)
+        for i in range(len(pr.layers)):
+            ops.cast_bf16(lat, lat_bf)
+            cat[:, :M].copy_(lat_bf)  # cross_attn_include_queries: keys = cat(latents, context) (ns2.py:1060-1061)
+            ops.gemm(lat_bf, P[f"pr{i}_q"], q, n=inner, epilogue=ops.EPI_BF16)
+            ops.gemm(cat, P[f"pr{i}_kv"], kv, n=2 * inner, epilogue=ops.EPI_BF16)
+            ops.attention(q, kv[:, :, :inner], kv[:, :, inner:], o, heads=H)
+            ops.gemm(o, P[f"pr{i}_o"], lat, n=D, epilogue=ops.EPI_F32, resid=lat)
+            ops.cast_bf16(lat, lat_bf)
+            ops.gemm(lat_bf, P[f"pr{i}_ff_w1"], g, n=2 * Dp, epilogue=ops.EPI_GEGLU, bias=P[f"pr{i}_ff_b1"])
+            ops.gemm(g, P[f"pr{i}_ff_w2"], lat, n=D, epilogue=ops.EPI_F32, bias=P[f"pr{i}_ff_b2"], resid=lat)
+        out = torch.empty(B, M, D, device=dev, dtype=torch.float32)
+        ops.rmsnorm_f32(lat, out, pr.norm.gamma.detach().float().contiguous())
+        return out
+
+    def precompute_conditioning(self, prompt: torch.Tensor, cond: torch.Tensor, length: int) -> dict:
+        """Everything in `forward` that depends on (prompt, cond) but not on the timestep or x:
+        prompt FiLM vector, perceiver latents, projected aligned condition (ns2.py:947-992)."""
+        assert self.condition_on_prompt
+        P, D = self.packed(), self.dim
+        B = prompt.shape[0]
+        dev = prompt.device
+        prompt = prompt.float().contiguous()
+        mean = ops.mean_rows(prompt, torch.empty(B, self.dim_prompt, device=dev))
+        lin = self.to_prompt_cond[1]
+        prompt_cond = ops.small_linear(mean, lin.weight.detach().float().contiguous(),
+                                       lin.bias.detach().float().contiguous(),
+                                       torch.empty(B, self.dim_time, device=dev), act=1)
+        tokens = self._perceiver(prompt)
+        L = cond.shape[-1]
+        c_bf = ops.transpose_cast(cond.float().contiguous(), torch.empty(B, L, self.dim_prompt, device=dev,
+                                                                         dtype=torch.bfloat16))
+        cond_proj = ops.gemm(c_bf, P["cond_w"], torch.empty(B, L, D, device=dev), n=D, epilogue=ops.EPI_F32,
+                             bias=P["cond_b"])
+        return {"prompt_cond": prompt_cond, "tokens": tokens, "cond_proj": cond_proj, "length": length}
+
+    # ----------------------------------------------------------------------------------------------
+    # forward
+    # ----------------------------------------------------------------------------------------------
+    def forward_with_cond_scale(self, *args, cond_scale=1., **kwargs):
+        """ns2.py:914-927: one forward, or conditional + null forwards combined when cond_scale != 1."""
+        logits = self.forward(*args, cond_drop_prob=0., **kwargs)
+        if cond_scale == 1.:
+            return logits
+        logits = logits.clone()  # the output workspace is reused by the next call
+        null_logits = self.forward(*args, cond_drop_prob=1., **kwargs)
+        return ops.cfg_combine(logits, null_logits, cond_scale, torch.empty_like(logits))
+
+    @torch.no_grad()
+    def forward(self, x, times, prompt=None, prompt_mask=None, cond=None, cond_drop_prob=None,
+                _conditioning: Optional[dict] = None):
+        """x (B, N, dim) fp32, times (B,) in [0, 1] -> (B, N, dim) fp32   (ns2.py:929-1000).
+
+        The returned tensor is a workspace owned by the model: it is overwritten by the next call with the
+        same (B, N).  Inference only (no autograd graph is recorded)."""
+        if prompt_mask is not None:
+            raise NotImplementedError("prompt_mask is unsupported (the reference itself fails on it, SURVEY T9)")
+        if not x.is_cuda:
+            raise RuntimeError("naturalspeech2_pytorch_b200.Model runs on CUDA (sm_100a) tensors only")
+        B, N, D = x.shape
+        assert D == self.dim, f"expected last dim {self.dim}, got {D}"
+        dev = x.device
+        P = self.packed()
+        ws = self._workspace(B, N, dev)
+        G, inner, H = self.wavenet_layers, self.inner, self.heads
+        cond_drop_prob = self.cond_drop_prob if cond_drop_prob is None else cond_drop_prob
+
+        # ---- time / prompt conditioning vector t: (B, dim_cond) ----
+        t = ws["t"]
+        tc = self.to_time_cond
+        ops.time_cond(times.float().contiguous(), tc[0].weights.detach().float().contiguous(),
+                      tc[1].weight.detach().float().contiguous(), tc[1].bias.detach().float().contiguous(),
+                      t[:, :self.dim_time])
+        c_tokens = None
+        x_add = None
+        if self.condition_on_prompt:
+            if _conditioning is None:
+                assert _exists(prompt), "prompt is required when condition_on_prompt=True"
+                assert _exists(cond), "cond is required when condition_on_prompt=True"
+                _conditioning = self.precompute_conditioning(prompt, cond, N)
+            drop_mask = _prob_mask_like((B,), cond_drop_prob, dev)
+            prompt_cond = torch.where(drop_mask[:, None], self.null_prompt_cond.detach().float(),
+                                      _conditioning["prompt_cond"])
+            t[:, self.dim_time:].copy_(prompt_cond)
+            c_tokens = torch.where(drop_mask[:, None, None], self.null_prompt_tokens.detach().float(),
+                                   _conditioning["tokens"])
+            cond_drop_mask = _prob_mask_like((B,), cond_drop_prob, dev)
+            cproj = _conditioning["cond_proj"]  # (B, L, D) token-major
+            cproj = torch.where(cond_drop_mask[:, None, None], self.null_cond.detach().float().t()[None], cproj)
+            L = cproj.shape[1]
+            if L > N:
+                cproj = cproj[:, :N]
+            elif L < N:
+                cproj = torch.nn.functional.pad(cproj, (0, 0, 0, N - L))  # pad_or_curtail_to_length (ns2.py:70-77)
+            x_add = cproj.contiguous()
+
+        # ---- all FiLM (gamma, beta) vectors in one GEMM ----
+        ops.cast_bf16(t, ws["t_bf"])
+        film = ops.gemm(ws["t_bf"], P["film_w"], ws["film"], n=P["film_w"].shape[0], epilogue=ops.EPI_F32,
+                        bias=P["film_b"])[0]  # (B, rows)
+
+        # ---- wavenet ----
+        x_bf = ops.cast_bf16(x.float().contiguous(), ws["x_bf"], add=x_add)
+        h = ops.gemm(x_bf, P["wn_init_w"], ws["h"], n=D, epilogue=ops.EPI_BF16, bias=P["wn_init_b"],
+                     segs=ops.conv3_segs(D))
+        segs = ops.conv3_segs(D) + [(0, 3 * D, D, 0, 1)]
+        dil = [2 ** i for i in range(G)]
+        src, bufs = h, (ws["wn_a"], ws["wn_b"])
+        for s in range(self.wavenet_stacks):
+            dst = bufs[s % 2]
+            ops.gemm(src, P[f"wn{s}_w"], dst, n=D, epilogue=ops.EPI_WAVENET, bias=P[f"wn{s}_b"],
+                     bias1_off=G * D, segs=segs, film=film[:, s * G * 2 * D:], film_group_stride=2 * D,
+                     groups=G, a_group_col_stride=0 if s == 0 else D, b_group_row_stride=D,
+                     out_group_col_stride=D, dil=dil)
+            src = dst
+        skip = ops.gemm(src, P["wn_skip_w"], ws["h"], n=D, epilogue=ops.EPI_BF16, bias=P["wn_skip_b"])
+        xr = ops.gemm(skip, P["wn_final_w"], ws["x_res"], n=D, epilogue=ops.EPI_F32, bias=P["wn_final_b"])
+
+        # ---- transformer ----
+        if c_tokens is not None:
+            ops.cast_bf16(c_tokens.contiguous(), ws["c_bf"])
+            ops.gemm(ws["c_bf"], P["x_kv_all"], ws["xkv"], n=self.depth * 2 * inner, epilogue=ops.EPI_BF16)
+        qkv, ao = ws["qkv"], ws["attn_o"]
+        Dp = ws["ff_g"].shape[-1]
+        npl = self._norms_per_layer
+        for l in range(self.depth):
+            fo = self._film_tr_off + l * npl * 2 * D
+            ops.rmsnorm_film(xr, ws["h"], film=film[:, fo:fo + 2 * D])
+            ops.gemm(ws["h"], P[f"l{l}_qkv"], qkv, n=3 * inner, epilogue=ops.EPI_BF16)
+            ops.attention(qkv[:, :, :inner], qkv[:, :, inner:2 * inner], qkv[:, :, 2 * inner:], ao, heads=H)
+            ops.gemm(ao, P[f"l{l}_o"], xr, n=D, epilogue=ops.EPI_F32, resid=xr)
+            j = 1
+            if c_tokens is not None:
+                fo2 = fo + 2 * D
+                ops.rmsnorm_film(xr, ws["h"], film=film[:, fo2:fo2 + 2 * D])
+                ops.gemm(ws["h"], P[f"l{l}_xq"], ws["xq"], n=inner, epilogue=ops.EPI_BF16)
+                kv = ws["xkv"][:, :, l * 2 * inner:(l + 1) * 2 * inner]
+                ops.attention(ws["xq"], kv[:, :, :inner], kv[:, :, inner:], ao, heads=H)
+                ops.gemm(ao, P[f"l{l}_xo"], xr, n=D, epilogue=ops.EPI_F32, resid=xr)
+                j = 2
+            fo3 = fo + j * 2 * D
+            ops.rmsnorm_film(xr, ws["h"], film=film[:, fo3:fo3 + 2 * D])
+            ops.gemm(ws["h"], P[f"l{l}_ff_w1"], ws["ff_g"], n=2 * Dp, epilogue=ops.EPI_GEGLU,
+                     bias=P[f"l{l}_ff_b1"])
+            ops.gemm(ws["ff_g"], P[f"l{l}_ff_wc"], ws["ff_c"], n=Dp, epilogue=ops.EPI_BF16,
+                     bias=P[f"l{l}_ff_bc"], segs=ops.conv3_segs(Dp))
+            ops.gemm(ws["ff_c"], P[f"l{l}_ff_w2"], xr, n=D, epilogue=ops.EPI_F32, bias=P[f"l{l}_ff_b2"],
+                     resid=xr)
+        ops.rmsnorm_film(xr, ws["h"], gamma=P["pred_gamma"])
+        return ops.gemm(ws["h"], P["pred_w"], ws["out"], n=D, epilogue=ops.EPI_F32)

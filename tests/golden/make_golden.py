@@ -1,0 +1,179 @@
+#!/usr/bin/env python
+"""Generate the golden fixtures in this directory from the REFERENCE implementation.
+
+Runs only in the authoring container: it imports lucidrains/naturalspeech2-pytorch from /root/reference
+(read-only) with `sys.modules` stubs for the third-party packages that are not installed,
+builds small `Model`s, fills their parameters with tests/param_fill.py (deterministic by state_dict key), runs
+the reference forward on CPU in fp64 / fp32 / autocast-bf16, and stores inputs + outputs as .npz.  The GPU box
+never sees /root/reference; it only reads the committed fixtures.
+
+    python tests/golden/make_golden.py
+"""
+from __future__ import annotations
+
+import sys
+import types
+from pathlib import Path
+
+import numpy as np
+import torch
+
+HERE = Path(__file__).resolve().parent
+ROOT = HERE.parent.parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+
+from param_fill import fill_module, seeded, seeded_uniform  # noqa: E402
+
+
+def import_reference(path="/root/reference"):
+    """Stub the seven missing third-party modules, then import the reference package."""
+    def stub(name, **attrs):
+        m = types.ModuleType(name)
+        for k, v in attrs.items():
+            setattr(m, k, v)
+        sys.modules[name] = m
+        return m
+
+    class _SoundStream(torch.nn.Module):
+        pass
+
+    class _EncodecWrapper(torch.nn.Module):
+        pass
+
+    stub("audiolm_pytorch", SoundStream=_SoundStream, EncodecWrapper=_EncodecWrapper)
+    stub("audiolm_pytorch.data", SoundDataset=object, get_dataloader=lambda *a, **k: None)
+    stub("accelerate", Accelerator=object)
+    stub("ema_pytorch", EMA=object)
+    stub("pyworld")
+    stub("inflect", engine=lambda: None)
+    stub("num2words", num2words=lambda *a, **k: "")
+    stub("num_to_words", num_to_word=lambda *a, **k: "")
+    sys.path.insert(0, path)
+    import naturalspeech2_pytorch  # noqa: F401
+    from naturalspeech2_pytorch import naturalspeech2_pytorch as ns2
+    return ns2
+
+
+CASES = {
+    # name: (model kwargs, B, N, prompt_len, cond_len)
+    "uncond_small": (dict(dim=128, depth=2, heads=2, wavenet_layers=3, wavenet_stacks=2), 2, 160, None, None),
+    "cond_small": (dict(dim=128, depth=2, heads=2, wavenet_layers=3, wavenet_stacks=2, dim_prompt=192,
+                        condition_on_prompt=True, resampler_depth=1), 2, 160, 40, 150),
+    "cond_samedim": (dict(dim=128, depth=1, heads=4, wavenet_layers=2, wavenet_stacks=2, dim_prompt=128,
+                          condition_on_prompt=True, resampler_depth=2, num_latents_m=16), 3, 130, 25, 200),
+    "readme_uncond": (dict(dim=128, depth=6), 1, 1024, None, None),
+}
+
+
+def to_np(sd):
+    return {k: v.detach().cpu().numpy() for k, v in sd.items()}
+
+
+def run_case(ns2, name, kwargs, B, N, Np, L):
+    torch.manual_seed(0)
+    model = ns2.Model(**kwargs).eval()
+    fill_module(model, seed=1234)
+    x = seeded((B, N, kwargs["dim"]), 11)
+    times = seeded_uniform((B,), 12)
+    inputs = {"x": x, "times": times}
+    fkw = {}
+    if kwargs.get("condition_on_prompt"):
+        inputs["prompt"] = seeded((B, Np, kwargs["dim_prompt"]), 13)
+        inputs["cond"] = seeded((B, kwargs["dim_prompt"], L), 14)
+        fkw = dict(prompt=inputs["prompt"], cond=inputs["cond"])
+    out = {}
+    with torch.no_grad():
+        out["out_fp32"] = model(x, times, **fkw)
+        m64 = ns2.Model(**kwargs).double().eval()
+        m64.load_state_dict({k: v.double() for k, v in model.state_dict().items()})
+        out["out_fp64"] = m64(x.double(), times.double(), **{k: v.double() for k, v in fkw.items()})
+        with torch.autocast("cpu", dtype=torch.bfloat16):
+            out["out_bf16_autocast"] = model(x, times, **fkw).float()
+        if kwargs.get("condition_on_prompt"):
+            out["out_fp64_null"] = m64(x.double(), times.double(), cond_drop_prob=1.,
+                                       **{k: v.double() for k, v in fkw.items()})
+            out["out_fp64_cfg3"] = m64.forward_with_cond_scale(
+                x.double(), times.double(), cond_scale=3., **{k: v.double() for k, v in fkw.items()})
+    e32 = (out["out_fp32"].double() - out["out_fp64"]).abs().max().item()
+    e16 = (out["out_bf16_autocast"].double() - out["out_fp64"]).abs().max().item()
+    print(f"{name}: params={sum(p.numel() for p in model.parameters())} out_std={out['out_fp64'].std():.3f} "
+          f"|fp32-fp64|max={e32:.2e} |bf16autocast-fp64|max={e16:.2e}")
+    arrays = {"in_" + k: v.numpy() for k, v in inputs.items()}
+    for k, v in out.items():
+        arrays[k] = v.numpy().astype(np.float64 if "fp64" in k else np.float32)
+    arrays["config"] = np.array(repr(sorted(kwargs.items())))
+    arrays["fill_seed"] = np.array(1234)
+    np.savez_compressed(HERE / f"model_{name}.npz", **arrays)
+    return model
+
+
+def diffusion_goldens(ns2):
+    """Loss with injected (times, noise) and a 4-step DDIM sample from fixed initial noise (uncond_small)."""
+    kwargs, B, N, _, _ = CASES["uncond_small"]
+    model = ns2.Model(**kwargs).eval()  # fp32: the wrapper draws float32 times (ns2.py:1621)
+    fill_module(model, seed=1234)
+    diff = ns2.NaturalSpeech2(model=model, target_sample_hz=24000, timesteps=4)
+    latents = seeded((B, N, kwargs["dim"]), 21)
+    # replicate ns2.py:1621-1666 with known times/noise by seeding torch's CPU generator and recording the draws
+    torch.manual_seed(77)
+    times = torch.zeros((B,)).float().uniform_(0, 1.)
+    noise = torch.randn_like(latents)
+    torch.manual_seed(77)
+    with torch.no_grad():
+        loss = diff(latents)
+    torch.manual_seed(78)
+    init = torch.randn((B, 64, kwargs["dim"]))
+    torch.manual_seed(78)
+    with torch.no_grad():
+        sample = diff.sample(length=64, batch_size=B)
+    print(f"diffusion: loss={loss.item():.6f} sample_std={sample.std():.3f}")
+    np.savez_compressed(HERE / "diffusion_uncond_small.npz", latents=latents.numpy(), times=times.numpy(),
+                        noise=noise.numpy(), loss=np.array(loss.item()), ddim_init=init.numpy(),
+                        ddim_out=sample.numpy(), timesteps=np.array(4))
+
+
+def rvq_goldens():
+    """Codes from the HF transformers port of Encodec's residual VQ (fp32 formula) on seeded codebooks.
+    Inputs are regenerated from seeds by param_fill.rvq_fixture_inputs(); only the outputs are stored."""
+    from transformers import EncodecConfig
+    from transformers.models.encodec.modeling_encodec import EncodecResidualVectorQuantizer
+    from param_fill import rvq_fixture_inputs
+    cfg = EncodecConfig()  # 24 kHz, codebook 1024 x 128
+    rvq = EncodecResidualVectorQuantizer(cfg).eval()
+    cb, variants = rvq_fixture_inputs()
+    Q = cb.shape[0]
+    assert (cfg.codebook_size, cfg.codebook_dim) == tuple(cb.shape[1:])
+    with torch.no_grad():
+        for q in range(Q):
+            rvq.layers[q].codebook.embed.copy_(cb[q])
+    out = {}
+    with torch.no_grad():
+        for name, fr in variants.items():
+            emb = fr.t()[None]  # (1, d, F)
+            bandwidth = Q * math_log2(cfg.codebook_size) * cfg.frame_rate / 1000.0
+            codes = rvq.encode(emb, bandwidth=bandwidth)  # (Q, 1, F)
+            assert codes.shape[0] == Q, codes.shape
+            dec = rvq.decode(codes)  # (1, d, F)
+            out[f"codes_{name}"] = codes[:, 0].t().contiguous().numpy().astype(np.int64)
+            if name == "random":
+                out[f"decoded_{name}"] = dec[0].t().contiguous().numpy()
+    np.savez_compressed(HERE / "rvq_encodec.npz", **out)
+    print("rvq:", {k: v.shape for k, v in out.items()})
+
+
+def math_log2(v):
+    import math
+    return math.log2(v)
+
+
+def main():
+    rvq_goldens()  # before the stubs: transformers probes the real `accelerate` module spec
+    ns2 = import_reference()
+    for name, (kwargs, B, N, Np, L) in CASES.items():
+        run_case(ns2, name, kwargs, B, N, Np, L)
+    diffusion_goldens(ns2)
+
+
+if __name__ == "__main__":
+    main()
