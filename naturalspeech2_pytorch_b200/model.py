@@ -204,6 +204,7 @@ class Model(nn.Module):
         self._packed_sig = None
         self._ws: Dict[tuple, Dict[str, torch.Tensor]] = {}
         self.freeze_packed = False  # set True to skip the per-call parameter-version check (inference loops)
+        self._prof = None           # bench.py: list collecting (op name, start event, end event)
 
     @property
     def device(self):
@@ -375,7 +376,9 @@ class Model(nn.Module):
         cat = torch.empty(B, ctx_len, D, device=dev, dtype=bf)  # [latents ; projected prompt]
         p_bf = ops.cast_bf16(prompt.contiguous().float(), torch.empty(B, Np, self.dim_prompt, device=dev, dtype=bf))
         if "pr_proj_w" in P:
-            ops.gemm(p_bf, P["pr_proj_w"], cat[:, M:], n=D, epilogue=ops.EPI_BF16, bias=P["pr_proj_b"])
+            proj = ops.gemm(p_bf, P["pr_proj_w"], torch.empty(B, Np, D, device=dev, dtype=bf), n=D,
+                            epilogue=ops.EPI_BF16, bias=P["pr_proj_b"])
+            cat[:, M:].copy_(proj)
         else:
             cat[:, M:].copy_(p_bf)
         lat = pr.latents.detach().float().unsqueeze(0).expand(B, M, D).contiguous()
@@ -420,6 +423,17 @@ class Model(nn.Module):
                              bias=P["cond_b"])
         return {"prompt_cond": prompt_cond, "tokens": tokens, "cond_proj": cond_proj, "length": length}
 
+    def _run(self, name, fn, *args, **kwargs):
+        """Call one kernel wrapper; when profiling is on, bracket it with CUDA events on the current stream."""
+        if self._prof is None:
+            return fn(*args, **kwargs)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        out = fn(*args, **kwargs)
+        b.record()
+        self._prof.append((name, a, b))
+        return out
+
     # ----------------------------------------------------------------------------------------------
     # forward
     # ----------------------------------------------------------------------------------------------
@@ -454,7 +468,7 @@ class Model(nn.Module):
         # ---- time / prompt conditioning vector t: (B, dim_cond) ----
         t = ws["t"]
         tc = self.to_time_cond
-        ops.time_cond(times.float().contiguous(), tc[0].weights.detach().float().contiguous(),
+        self._run("time_cond", ops.time_cond, times.float().contiguous(), tc[0].weights.detach().float().contiguous(),
                       tc[1].weight.detach().float().contiguous(), tc[1].bias.detach().float().contiguous(),
                       t[:, :self.dim_time])
         c_tokens = None
@@ -481,56 +495,56 @@ class Model(nn.Module):
             x_add = cproj.contiguous()
 
         # ---- all FiLM (gamma, beta) vectors in one GEMM ----
-        ops.cast_bf16(t, ws["t_bf"])
-        film = ops.gemm(ws["t_bf"], P["film_w"], ws["film"], n=P["film_w"].shape[0], epilogue=ops.EPI_F32,
+        self._run("cast", ops.cast_bf16, t, ws["t_bf"])
+        film = self._run("film", ops.gemm, ws["t_bf"], P["film_w"], ws["film"], n=P["film_w"].shape[0], epilogue=ops.EPI_F32,
                         bias=P["film_b"])[0]  # (B, rows)
 
         # ---- wavenet ----
-        x_bf = ops.cast_bf16(x.float().contiguous(), ws["x_bf"], add=x_add)
-        h = ops.gemm(x_bf, P["wn_init_w"], ws["h"], n=D, epilogue=ops.EPI_BF16, bias=P["wn_init_b"],
+        x_bf = self._run("cast", ops.cast_bf16, x.float().contiguous(), ws["x_bf"], add=x_add)
+        h = self._run("wn_init", ops.gemm, x_bf, P["wn_init_w"], ws["h"], n=D, epilogue=ops.EPI_BF16, bias=P["wn_init_b"],
                      segs=ops.conv3_segs(D))
         segs = ops.conv3_segs(D) + [(0, 3 * D, D, 0, 1)]
         dil = [2 ** i for i in range(G)]
         src, bufs = h, (ws["wn_a"], ws["wn_b"])
         for s in range(self.wavenet_stacks):
             dst = bufs[s % 2]
-            ops.gemm(src, P[f"wn{s}_w"], dst, n=D, epilogue=ops.EPI_WAVENET, bias=P[f"wn{s}_b"],
+            self._run("wn_stack", ops.gemm, src, P[f"wn{s}_w"], dst, n=D, epilogue=ops.EPI_WAVENET, bias=P[f"wn{s}_b"],
                      bias1_off=G * D, segs=segs, film=film[:, s * G * 2 * D:], film_group_stride=2 * D,
                      groups=G, a_group_col_stride=0 if s == 0 else D, b_group_row_stride=D,
                      out_group_col_stride=D, dil=dil)
             src = dst
-        skip = ops.gemm(src, P["wn_skip_w"], ws["h"], n=D, epilogue=ops.EPI_BF16, bias=P["wn_skip_b"])
-        xr = ops.gemm(skip, P["wn_final_w"], ws["x_res"], n=D, epilogue=ops.EPI_F32, bias=P["wn_final_b"])
+        skip = self._run("wn_skip", ops.gemm, src, P["wn_skip_w"], ws["h"], n=D, epilogue=ops.EPI_BF16, bias=P["wn_skip_b"])
+        xr = self._run("wn_final", ops.gemm, skip, P["wn_final_w"], ws["x_res"], n=D, epilogue=ops.EPI_F32, bias=P["wn_final_b"])
 
         # ---- transformer ----
         if c_tokens is not None:
-            ops.cast_bf16(c_tokens.contiguous(), ws["c_bf"])
-            ops.gemm(ws["c_bf"], P["x_kv_all"], ws["xkv"], n=self.depth * 2 * inner, epilogue=ops.EPI_BF16)
+            self._run("cast", ops.cast_bf16, c_tokens.contiguous(), ws["c_bf"])
+            self._run("x_kv", ops.gemm, ws["c_bf"], P["x_kv_all"], ws["xkv"], n=self.depth * 2 * inner, epilogue=ops.EPI_BF16)
         qkv, ao = ws["qkv"], ws["attn_o"]
         Dp = ws["ff_g"].shape[-1]
         npl = self._norms_per_layer
         for l in range(self.depth):
             fo = self._film_tr_off + l * npl * 2 * D
-            ops.rmsnorm_film(xr, ws["h"], film=film[:, fo:fo + 2 * D])
-            ops.gemm(ws["h"], P[f"l{l}_qkv"], qkv, n=3 * inner, epilogue=ops.EPI_BF16)
-            ops.attention(qkv[:, :, :inner], qkv[:, :, inner:2 * inner], qkv[:, :, 2 * inner:], ao, heads=H)
-            ops.gemm(ao, P[f"l{l}_o"], xr, n=D, epilogue=ops.EPI_F32, resid=xr)
+            self._run("norm", ops.rmsnorm_film, xr, ws["h"], film=film[:, fo:fo + 2 * D])
+            self._run("qkv", ops.gemm, ws["h"], P[f"l{l}_qkv"], qkv, n=3 * inner, epilogue=ops.EPI_BF16)
+            self._run("attn", ops.attention, qkv[:, :, :inner], qkv[:, :, inner:2 * inner], qkv[:, :, 2 * inner:], ao, heads=H)
+            self._run("attn_out", ops.gemm, ao, P[f"l{l}_o"], xr, n=D, epilogue=ops.EPI_F32, resid=xr)
             j = 1
             if c_tokens is not None:
                 fo2 = fo + 2 * D
-                ops.rmsnorm_film(xr, ws["h"], film=film[:, fo2:fo2 + 2 * D])
-                ops.gemm(ws["h"], P[f"l{l}_xq"], ws["xq"], n=inner, epilogue=ops.EPI_BF16)
+                self._run("norm", ops.rmsnorm_film, xr, ws["h"], film=film[:, fo2:fo2 + 2 * D])
+                self._run("x_q", ops.gemm, ws["h"], P[f"l{l}_xq"], ws["xq"], n=inner, epilogue=ops.EPI_BF16)
                 kv = ws["xkv"][:, :, l * 2 * inner:(l + 1) * 2 * inner]
-                ops.attention(ws["xq"], kv[:, :, :inner], kv[:, :, inner:], ao, heads=H)
-                ops.gemm(ao, P[f"l{l}_xo"], xr, n=D, epilogue=ops.EPI_F32, resid=xr)
+                self._run("x_attn", ops.attention, ws["xq"], kv[:, :, :inner], kv[:, :, inner:], ao, heads=H)
+                self._run("x_out", ops.gemm, ao, P[f"l{l}_xo"], xr, n=D, epilogue=ops.EPI_F32, resid=xr)
                 j = 2
             fo3 = fo + j * 2 * D
-            ops.rmsnorm_film(xr, ws["h"], film=film[:, fo3:fo3 + 2 * D])
-            ops.gemm(ws["h"], P[f"l{l}_ff_w1"], ws["ff_g"], n=2 * Dp, epilogue=ops.EPI_GEGLU,
+            self._run("norm", ops.rmsnorm_film, xr, ws["h"], film=film[:, fo3:fo3 + 2 * D])
+            self._run("ff_in", ops.gemm, ws["h"], P[f"l{l}_ff_w1"], ws["ff_g"], n=2 * Dp, epilogue=ops.EPI_GEGLU,
                      bias=P[f"l{l}_ff_b1"])
-            ops.gemm(ws["ff_g"], P[f"l{l}_ff_wc"], ws["ff_c"], n=Dp, epilogue=ops.EPI_BF16,
+            self._run("ff_conv", ops.gemm, ws["ff_g"], P[f"l{l}_ff_wc"], ws["ff_c"], n=Dp, epilogue=ops.EPI_BF16,
                      bias=P[f"l{l}_ff_bc"], segs=ops.conv3_segs(Dp))
-            ops.gemm(ws["ff_c"], P[f"l{l}_ff_w2"], xr, n=D, epilogue=ops.EPI_F32, bias=P[f"l{l}_ff_b2"],
+            self._run("ff_out", ops.gemm, ws["ff_c"], P[f"l{l}_ff_w2"], xr, n=D, epilogue=ops.EPI_F32, bias=P[f"l{l}_ff_b2"],
                      resid=xr)
-        ops.rmsnorm_film(xr, ws["h"], gamma=P["pred_gamma"])
-        return ops.gemm(ws["h"], P["pred_w"], ws["out"], n=D, epilogue=ops.EPI_F32)
+        self._run("norm", ops.rmsnorm_film, xr, ws["h"], gamma=P["pred_gamma"])
+        return self._run("pred", ops.gemm, ws["h"], P["pred_w"], ws["out"], n=D, epilogue=ops.EPI_F32)

@@ -72,7 +72,7 @@ def causal_conv1d(x, w, b, dilation=1):
     y = np.zeros((B, O, N), dtype=x.dtype)
     for t in range(K):
         # tap t reads x_padded[n + t*dilation] = x[n - (K-1-t)*dilation]
-        y += np.einsum("oi,bin->bon", w[:, :, t], xp[:, :, t * dilation:t * dilation + N])
+        y += np.matmul(w[:, :, t], xp[:, :, t * dilation:t * dilation + N])  # (O,I) @ (B,I,N) -> (B,O,N)
     return y + b[None, :, None]
 
 
@@ -93,11 +93,11 @@ def rmsnorm(x, gamma=None, film: Optional[np.ndarray] = None):
 def attend(q, k, v):
     """Attend.forward, attend.py:112-155 with mask=None, causal=False, dropout=0: softmax(q k^T / sqrt(d)) v."""
     scale = q.shape[-1] ** -0.5
-    sim = np.einsum("bhid,bhjd->bhij", q, k) * scale
+    sim = np.matmul(q, k.transpose(0, 1, 3, 2)) * scale
     sim = sim - sim.max(axis=-1, keepdims=True)
     p = np.exp(sim)
     p = p / p.sum(axis=-1, keepdims=True)
-    return np.einsum("bhij,bhjd->bhid", p, v)
+    return np.matmul(p, v)
 
 
 def attention(P: Params, prefix: str, x, heads, context=None, include_queries=False):
