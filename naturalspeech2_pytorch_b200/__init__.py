@@ -6,5 +6,8 @@ Public names mirror naturalspeech2_pytorch/__init__.py:8-24 for the path this pa
 """
 from . import _lib, ops  # noqa: F401
 from .model import Model  # noqa: F401
+from .diffusion import NaturalSpeech2  # noqa: F401
+from .codec import EncodecRVQ  # noqa: F401
+from . import parallel  # noqa: F401
 
 __version__ = "0.1.0"

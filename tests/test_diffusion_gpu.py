@@ -1,0 +1,69 @@
+"""GPU: NaturalSpeech2.forward (loss) and DDIM sampling against goldens generated from the reference."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import GOLDEN, build_model, err_stats, load_model_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def _wrapper(timesteps=4):
+    from naturalspeech2_pytorch_b200 import NaturalSpeech2
+    _, kwargs, seed = load_model_golden("uncond_small")
+    model = build_model(kwargs, seed, device="cuda")
+    return NaturalSpeech2(model, target_sample_hz=24000, timesteps=timesteps)
+
+
+def test_training_loss_matches_reference():
+    z = np.load(GOLDEN / "diffusion_uncond_small.npz")
+    ns = _wrapper()
+    loss = ns(torch.from_numpy(z["latents"]).cuda(), times=torch.from_numpy(z["times"]),
+              noise=torch.from_numpy(z["noise"]))
+    ref = float(z["loss"])
+    print(f"loss ours={float(loss):.6f} reference={ref:.6f}")
+    # the loss averages 2*160*128 squared errors of O(1) values computed with bf16 operands: 1e-3 relative
+    assert abs(float(loss) - ref) < 1e-3 * abs(ref) + 1e-5, (float(loss), ref)
+    # p_losses is an alias (BASELINE.json names it; the reference inlines it)
+    assert ns.p_losses.__func__ is ns.forward.__func__
+
+
+def test_ddim_sample_matches_reference():
+    z = np.load(GOLDEN / "diffusion_uncond_small.npz")
+    ns = _wrapper(int(z["timesteps"]))
+    out = ns.sample(length=64, batch_size=2, noise=torch.from_numpy(z["ddim_init"])).cpu().numpy()
+    emax, erms = err_stats(out, z["ddim_out"])
+    print(f"ddim 4 steps: max={emax:.3e} rms={erms:.3e} (sample std {z['ddim_out'].std():.2f})")
+    assert emax < 1.5e-1 and erms < 2.5e-2, (emax, erms)  # 4 chained denoiser calls, bf16 operands
+    # default path (fresh noise) runs and is finite
+    assert torch.isfinite(ns.sample(length=64, batch_size=1)).all()
+
+
+def test_sample_with_codec_roundtrip():
+    from naturalspeech2_pytorch_b200 import EncodecRVQ, NaturalSpeech2
+    _, kwargs, seed = load_model_golden("uncond_small")
+    model = build_model(kwargs, seed, device="cuda")
+    codec = EncodecRVQ(torch.randn(8, 1024, 128)).cuda()
+    ns = NaturalSpeech2(model, codec, timesteps=2)
+    latents = torch.randn(2, 160, 128, device="cuda")
+    loss = ns(latents)
+    assert loss.ndim == 0 and torch.isfinite(loss)
+    assert ns.sample(length=64, batch_size=2).shape == (2, 64, 128)  # no decoder plugged in -> latents
+    with pytest.raises(NotImplementedError):
+        ns(torch.randn(2, 3200, device="cuda"))  # raw audio needs an encoder callable
+
+
+def test_conditional_requires_conditioning():
+    from naturalspeech2_pytorch_b200 import NaturalSpeech2
+    _, kwargs, seed = load_model_golden("cond_small")
+    model = build_model(kwargs, seed, device="cuda")
+    ns = NaturalSpeech2(model, target_sample_hz=24000, timesteps=2)
+    z, _, _ = load_model_golden("cond_small")
+    with pytest.raises(NotImplementedError):
+        ns(torch.randn(2, 160, 128, device="cuda"))
+    prompt = torch.from_numpy(z["in_prompt"]).cuda()
+    cond = torch.from_numpy(z["in_cond"]).cuda()
+    loss = ns(torch.randn(2, 160, 128, device="cuda"), prompt_enc=prompt, cond=cond)
+    assert torch.isfinite(loss)
+    out = ns.sample(length=160, prompt_enc=prompt, cond=cond, cond_scale=1.5)
+    assert out.shape == (2, 160, 128) and torch.isfinite(out).all()
