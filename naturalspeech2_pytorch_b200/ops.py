@@ -33,7 +33,7 @@ def _req(t: torch.Tensor, dtype: torch.dtype, name: str) -> None:
         raise ValueError(f"{name} must be a CUDA tensor (the ns2_b200 ops have no CPU path)")
     if t.dtype != dtype:
         raise ValueError(f"{name} must be {dtype}, got {t.dtype}")
-    if t.dim() > 0 and t.stride(-1) != 1:
+    if t.dim() > 0 and t.shape[-1] > 1 and t.stride(-1) != 1:
         raise ValueError(f"{name} must be contiguous in its last dimension")
 
 

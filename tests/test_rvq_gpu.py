@@ -67,11 +67,23 @@ def test_rvq_full_size_properties():
     first = cb.cuda()[0][codes[:65536, 0]]
     again, _ = codec.quantize(first)
     assert torch.equal(again[:, 0], codes[:65536, 0])
-    # residual norms never increase across stages (each stage picks the nearest codeword incl. its distance to 0? no:
-    # property used: quantisation error after all stages is below the error after the first stage, on average)
-    err1 = (x[:65536] - first).norm(dim=-1).mean()
-    err8 = (x[:65536] - emb[:65536]).norm(dim=-1).mean()
-    assert float(err8) < float(err1)
+    # decode is the in-order sum of the looked-up codewords (checked with torch gathers at full size)
+    cbd = cb.cuda()
+    acc = torch.zeros_like(x)
+    for q in range(8):
+        acc = acc + cbd[q][codes[:, q]]
+    assert torch.equal(acc, emb)
+    # per-stage optimality at full size: the chosen codeword is at least as close to the stage's residual as
+    # 4 random other codewords (fp32 check with a rounding allowance; the exact claim is tested on the sample)
+    r = x.clone()
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    for q in range(8):
+        chosen = cbd[q][codes[:, q]]
+        d_best = (r - chosen).square().sum(-1)
+        for _ in range(4):
+            other = cbd[q][torch.randint(0, 1024, (F,), device="cuda", generator=gen)]
+            assert bool(((r - other).square().sum(-1) >= d_best * (1 - 1e-5)).all())
+        r = r - chosen
     # a random 4096-frame sample is bit-exact against the oracle
     idx = torch.randperm(F, generator=torch.Generator().manual_seed(0))[:4096]
     ref = rvq_oracle.encode(x[idx.cuda()].cpu().numpy(), cb.numpy())

@@ -1,0 +1,94 @@
+#!/usr/bin/env python
+"""Launch each hot kernel a few times at the cfg2 shapes (B=32, N=1024, D=512) — the target of
+`ncu --set full -k regex:...` captures.  Prints CUDA-event timings when run without ncu."""
+import sys
+from pathlib import Path
+
+import torch
+
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+from naturalspeech2_pytorch_b200 import ops  # noqa: E402
+
+B, N, D, H, Di, Dp = 32, 1024, 512, 8, 1365, 1408
+dev = "cuda"
+bf = torch.bfloat16
+which = set(sys.argv[1:]) or {"conv", "attn", "wavenet", "ffin", "ffout", "qkv", "norm", "rvq"}
+reps = 3
+
+
+def timeit(name, fn, flops=None, bytes_=None):
+    fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / reps
+    extra = ""
+    if flops:
+        extra += f" {flops / ms / 1e9:.0f} TFLOP/s"
+    if bytes_:
+        extra += f" {bytes_ / ms / 1e6:.0f} GB/s"
+    print(f"{name}: {ms:.4f} ms{extra}", flush=True)
+
+
+torch.manual_seed(0)
+if "conv" in which:
+    g = (torch.randn(B, N, Dp, device=dev) * 0.5).to(bf)
+    wc = (torch.randn(Dp, 3 * Dp, device=dev) * 0.02).to(bf)
+    bc = torch.randn(Dp, device=dev)
+    out = torch.empty(B, N, Dp, device=dev, dtype=bf)
+    timeit("ff_conv gemm<256,1,BF16>", lambda: ops.gemm(g, wc, out, n=Dp, epilogue=ops.EPI_BF16, bias=bc,
+                                                         segs=ops.conv3_segs(Dp)), flops=2.0 * B * N * Di * 3 * Di)
+if "attn" in which:
+    qkv = torch.randn(B, N, 3 * H * 64, device=dev).to(bf)
+    o = torch.empty(B, N, H * 64, device=dev, dtype=bf)
+    timeit("attn_fwd", lambda: ops.attention(qkv[:, :, :512], qkv[:, :, 512:1024], qkv[:, :, 1024:], o, heads=H),
+           flops=4.0 * B * H * N * N * 64)
+if "wavenet" in which:
+    G = 8
+    x = (torch.randn(B, N, G * D, device=dev) * 0.5).to(bf)
+    wp = (torch.randn(G * D, 4 * D, device=dev) * 0.02).to(bf)
+    bias = torch.randn(2 * G * D, device=dev)
+    film = torch.randn(B, G * 2 * D, device=dev)
+    out = torch.empty(B, N, G * D, device=dev, dtype=bf)
+    segs = ops.conv3_segs(D) + [(0, 3 * D, D, 0, 1)]
+    timeit("wavenet stack gemm<128,2,WAVENET>",
+           lambda: ops.gemm(x, wp, out, n=D, epilogue=ops.EPI_WAVENET, bias=bias, bias1_off=G * D, segs=segs,
+                            film=film, film_group_stride=2 * D, groups=G, a_group_col_stride=D,
+                            b_group_row_stride=D, out_group_col_stride=D, dil=[2 ** i for i in range(G)]),
+           flops=2.0 * B * N * D * 4 * D * G)
+if "ffin" in which:
+    h = torch.randn(B, N, D, device=dev).to(bf)
+    w1 = (torch.randn(2 * Dp, D, device=dev) * 0.04).to(bf)
+    b1 = torch.randn(2 * Dp, device=dev)
+    out = torch.empty(B, N, Dp, device=dev, dtype=bf)
+    timeit("ff_in gemm<256,1,GEGLU>", lambda: ops.gemm(h, w1, out, n=2 * Dp, epilogue=ops.EPI_GEGLU, bias=b1),
+           flops=2.0 * B * N * D * 2 * Di)
+if "ffout" in which:
+    c = torch.randn(B, N, Dp, device=dev).to(bf)
+    w2 = (torch.randn(D, Dp, device=dev) * 0.03).to(bf)
+    b2 = torch.randn(D, device=dev)
+    xr = torch.randn(B, N, D, device=dev)
+    timeit("ff_out gemm<128,1,F32+resid>", lambda: ops.gemm(c, w2, xr, n=D, epilogue=ops.EPI_F32, bias=b2, resid=xr),
+           flops=2.0 * B * N * Di * D)
+if "qkv" in which:
+    h = torch.randn(B, N, D, device=dev).to(bf)
+    w = (torch.randn(1536, D, device=dev) * 0.04).to(bf)
+    out = torch.empty(B, N, 1536, device=dev, dtype=bf)
+    timeit("qkv gemm<256,1,BF16>", lambda: ops.gemm(h, w, out, n=1536, epilogue=ops.EPI_BF16), flops=2.0 * B * N * D * 1536)
+if "norm" in which:
+    x = torch.randn(B, N, D, device=dev)
+    film = torch.randn(B, 2 * D, device=dev)
+    out = torch.empty(B, N, D, device=dev, dtype=bf)
+    timeit("rmsnorm_film", lambda: ops.rmsnorm_film(x, out, film=film), bytes_=B * N * D * 6.0)
+if "rvq" in which:
+    cb = torch.randn(8, 1024, 128, device=dev)
+    prep = ops.rvq_prepare(cb)
+    F = 1 << 20
+    x = torch.randn(F, 128, device=dev)
+    codes = torch.empty(F, 8, device=dev, dtype=torch.int64)
+    timeit("rvq_encode 1M x 8 x 1024", lambda: ops.rvq_encode(x, cb, prep, codes=codes), flops=2.0 * F * 8 * 1024 * 128)
+    print(f"  -> {F * 8 / 1e6:.1f} Mcodes per launch")
