@@ -9,7 +9,8 @@
 //   warp 4     TMA producer: Q once, then K_j / V_j tiles (128 keys x 64) through a 2-stage ring
 //   warp 5     tcgen05.mma issuer: S_j = Q.K_j^T (both K-major), O_j = P_j.V_j (V is the MN-major operand:
 //              its rows are keys = the reduction dimension, so no transpose of V is ever materialised)
-// S and O_j are double-buffered in TMEM so S_{j+1} is computed while the softmax of tile j runs.
+// O_j is double-buffered in TMEM; S_{j+1} is issued as soon as the softmax warps have consumed S_j, ahead of
+// P_j.V_j.  Two CTAs are co-resident per SM so one CTA's softmax overlaps the other's MMAs.
 #include "ptx.cuh"
 #include "host_common.h"
 #include "../../include/ns2_b200.h"
@@ -30,12 +31,12 @@ constexpr int P_BYTES = BQ * BKV * 2;        // 32 KB (two 64-key swizzle atoms 
 constexpr int OFF_Q = 0;
 constexpr int OFF_K = OFF_Q + Q_BYTES;                 // 2 stages
 constexpr int OFF_V = OFF_K + 2 * KV_BYTES;            // 2 stages
-constexpr int OFF_P = OFF_V + 2 * KV_BYTES;            // 2 buffers
-constexpr int OFF_BAR = OFF_P + 2 * P_BYTES;
-constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
-constexpr int TMEM_COLS = 512;
-constexpr int TM_S = 0;     // S buffers at columns 0 and 128
-constexpr int TM_O = 256;   // O_j buffers at columns 256 and 320
+constexpr int OFF_P = OFF_V + 2 * KV_BYTES;            // single buffer
+constexpr int OFF_BAR = OFF_P + P_BYTES;
+constexpr int SMEM_BYTES = OFF_BAR + 256;              // 112.25 KB -> two CTAs per SM
+constexpr int TMEM_COLS = 256;                         // two CTAs per SM share the 512 columns
+constexpr int TM_S = 0;     // S at columns [0, 128)
+constexpr int TM_O = 128;   // O_j buffers at columns 128 and 192
 }  // namespace attn
 
 struct AttnDev {
@@ -46,19 +47,25 @@ struct AttnDev {
   float scale_log2e;
 };
 
-__global__ void __launch_bounds__(192, 1) attn_fwd_kernel(const __grid_constant__ AttnDev p) {
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// Two CTAs are resident per SM (112 KB smem, 256 TMEM columns, <=170 registers each): while one CTA's softmax
+// warps occupy the MUFU/FMA pipes, the other CTA's MMAs occupy the tensor core.
+__global__ void __launch_bounds__(192, 2) attn_fwd_kernel(const __grid_constant__ AttnDev p) {
   using namespace attn;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                             ~static_cast<uintptr_t>(1023));
+  extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
   uint64_t* q_full = bars + 0;
   uint64_t* kv_full = bars + 1;   // [2]
   uint64_t* kv_empty = bars + 3;  // [2]
-  uint64_t* s_full = bars + 5;    // [2]
-  uint64_t* p_full = bars + 7;    // [2]
-  uint64_t* o_full = bars + 9;    // [2]
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 11);
+  uint64_t* s_full = bars + 5;
+  uint64_t* p_full = bars + 6;
+  uint64_t* o_full = bars + 7;    // [2]
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 9);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * BQ;
@@ -66,6 +73,10 @@ __global__ void __launch_bounds__(192, 1) attn_fwd_kernel(const __grid_constant_
   const int b = blockIdx.z;
   const int T = (p.kv_len + BKV - 1) / BKV;
 
+  if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) {
+    printf("ns2 attn: dynamic shared memory is not 1024-byte aligned\n");
+    __trap();
+  }
   if (warp == 4 && lane == 0) {
     tma_prefetch_desc(&p.tmQ);
     tma_prefetch_desc(&p.tmK);
@@ -73,11 +84,11 @@ __global__ void __launch_bounds__(192, 1) attn_fwd_kernel(const __grid_constant_
   }
   if (warp == 5 && lane == 0) {
     mbar_init(smem_u32(q_full), 1);
+    mbar_init(smem_u32(s_full), 1);
+    mbar_init(smem_u32(p_full), 128);
     for (int i = 0; i < 2; ++i) {
       mbar_init(smem_u32(&kv_full[i]), 1);
       mbar_init(smem_u32(&kv_empty[i]), 1);
-      mbar_init(smem_u32(&s_full[i]), 1);
-      mbar_init(smem_u32(&p_full[i]), 128);
       mbar_init(smem_u32(&o_full[i]), 1);
     }
     fence_barrier_init();
@@ -109,6 +120,7 @@ __global__ void __launch_bounds__(192, 1) attn_fwd_kernel(const __grid_constant_
       constexpr uint32_t idesc_s = umma_idesc_f16(BQ, BKV, 1, 0, 0);
       constexpr uint32_t idesc_o = umma_idesc_f16(BQ, DH, 1, 0, /*V is MN-major*/ 1);
       const uint64_t dq = umma_desc_sw128(smem_u32(smem + OFF_Q), 16, 1024);
+      const uint32_t pbase = smem_u32(smem + OFF_P);
       auto issue_s = [&](int j) {
         const int st = j & 1;
         mbar_wait(smem_u32(&kv_full[st]), (j >> 1) & 1);
@@ -116,18 +128,17 @@ __global__ void __launch_bounds__(192, 1) attn_fwd_kernel(const __grid_constant_
         const uint64_t dk = umma_desc_sw128(smem_u32(smem + OFF_K + st * KV_BYTES), 16, 1024);
 #pragma unroll
         for (int k = 0; k < DH / 16; ++k)
-          tc_mma_f16(tmem_base + TM_S + st * BKV, dq + 2 * k, dk + 2 * k, idesc_s, k > 0);
-        tc_commit(smem_u32(&s_full[st]));
+          tc_mma_f16(tmem_base + TM_S, dq + 2 * k, dk + 2 * k, idesc_s, k > 0);
+        tc_commit(smem_u32(s_full));
       };
       mbar_wait(smem_u32(q_full), 0);
       issue_s(0);
       for (int j = 0; j < T; ++j) {
         const int st = j & 1;
-        const uint32_t ph = (j >> 1) & 1;
-        if (j + 1 < T) issue_s(j + 1);  // overlaps the softmax of tile j
-        mbar_wait(smem_u32(&p_full[st]), ph);
+        // P_j is in smem and the softmax warps are done reading S_j
+        mbar_wait(smem_u32(p_full), j & 1);
         tc_fence_after();
-        const uint32_t pbase = smem_u32(smem + OFF_P + st * P_BYTES);
+        if (j + 1 < T) issue_s(j + 1);  // runs ahead of P_j.V_j so the next softmax can start early
         const uint32_t vbase = smem_u32(smem + OFF_V + st * KV_BYTES);
 #pragma unroll
         for (int k = 0; k < BKV / 16; ++k) {
@@ -145,86 +156,102 @@ __global__ void __launch_bounds__(192, 1) attn_fwd_kernel(const __grid_constant_
     // ================================ softmax warps ===============================
     const int row = warp * 32 + lane;
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+    const float c = p.scale_log2e;
     float o_acc[DH];
 #pragma unroll
     for (int i = 0; i < DH; ++i) o_acc[i] = 0.f;
     float m_run = -INFINITY, l_run = 0.f, a_prev = 0.f;
+    uint8_t* prow = smem + OFF_P + row * 128;
 
-    auto accumulate_o = [&](int jprev, float a) {
+    auto accumulate_o = [&](int jprev, float a) {  // o_full[jprev & 1] has already been waited on
       const int st = jprev & 1;
-      mbar_wait(smem_u32(&o_full[st]), (jprev >> 1) & 1);
-      tc_fence_after();
       uint32_t r0[32], r1[32];
       tmem_ld32(lane_addr + TM_O + st * DH, r0);
       tmem_ld32(lane_addr + TM_O + st * DH + 32, r1);
       tmem_ld_wait();
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
-        o_acc[i] = o_acc[i] * a + __uint_as_float(r0[i]);
-        o_acc[32 + i] = o_acc[32 + i] * a + __uint_as_float(r1[i]);
+        o_acc[i] = fmaf(o_acc[i], a, __uint_as_float(r0[i]));
+        o_acc[32 + i] = fmaf(o_acc[32 + i], a, __uint_as_float(r1[i]));
       }
     };
 
     for (int j = 0; j < T; ++j) {
-      const int st = j & 1;
-      mbar_wait(smem_u32(&s_full[st]), (j >> 1) & 1);
+      mbar_wait(smem_u32(s_full), j & 1);
       tc_fence_after();
       const int valid = p.kv_len - j * BKV;  // columns >= valid are padding keys
-      // pass 1: row maximum
+      const bool full = valid >= BKV;
+      // pass 1: row maximum of the raw scores
       float m_tile = -INFINITY;
 #pragma unroll 1
-      for (int c = 0; c < BKV / 32; ++c) {
+      for (int cc = 0; cc < BKV / 32; ++cc) {
         uint32_t r[32];
-        tmem_ld32(lane_addr + TM_S + st * BKV + c * 32, r);
+        tmem_ld32(lane_addr + TM_S + cc * 32, r);
         tmem_ld_wait();
+        if (full) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float s = (c * 32 + i < valid) ? __uint_as_float(r[i]) : -INFINITY;
-          m_tile = fmaxf(m_tile, s);
+          for (int i = 0; i < 32; ++i) m_tile = fmaxf(m_tile, __uint_as_float(r[i]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (cc * 32 + i < valid) m_tile = fmaxf(m_tile, __uint_as_float(r[i]));
         }
       }
-      const float m_new = fmaxf(m_run, m_tile * p.scale_log2e);
-      const float a = exp2f(m_run - m_new);  // 0 on the first tile (m_run = -inf)
+      const float m_new = fmaxf(m_run, m_tile * c);
+      const float a = ex2_approx(m_run - m_new);  // 0 on the first tile (m_run = -inf)
+      if (j > 0) {
+        // P.V of the previous tile has retired: the P buffer is free and O_{j-1} can be read
+        mbar_wait(smem_u32(&o_full[(j - 1) & 1]), ((j - 1) >> 1) & 1);
+        tc_fence_after();
+      }
       // pass 2: probabilities -> bf16 -> swizzled smem; row sum in fp32
       float l_tile = 0.f;
-      uint8_t* prow = smem + OFF_P + st * P_BYTES + row * 128;
 #pragma unroll 1
-      for (int c = 0; c < BKV / 32; ++c) {
+      for (int cc = 0; cc < BKV / 32; ++cc) {
         uint32_t r[32];
-        tmem_ld32(lane_addr + TM_S + st * BKV + c * 32, r);
+        tmem_ld32(lane_addr + TM_S + cc * 32, r);
         tmem_ld_wait();
         uint32_t pk[16];
+        if (full) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int c0 = c * 32 + 2 * i;
-          float p0 = (c0 < valid) ? exp2f(__uint_as_float(r[2 * i]) * p.scale_log2e - m_new) : 0.f;
-          float p1 =
-              (c0 + 1 < valid) ? exp2f(__uint_as_float(r[2 * i + 1]) * p.scale_log2e - m_new) : 0.f;
-          // the P.V product consumes bf16-rounded probabilities; sum the same rounded values so the
-          // normaliser matches the numerator exactly
-          const __nv_bfloat162 pb = __floats2bfloat162_rn(p0, p1);
-          l_tile += __bfloat162float(pb.x) + __bfloat162float(pb.y);
-          pk[i] = *reinterpret_cast<const uint32_t*>(&pb);
+          for (int i = 0; i < 16; ++i) {
+            const float p0 = ex2_approx(fmaf(__uint_as_float(r[2 * i]), c, -m_new));
+            const float p1 = ex2_approx(fmaf(__uint_as_float(r[2 * i + 1]), c, -m_new));
+            l_tile += p0 + p1;
+            pk[i] = pack_bf16x2(p0, p1);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int c0 = cc * 32 + 2 * i;
+            const float p0 = (c0 < valid) ? ex2_approx(fmaf(__uint_as_float(r[2 * i]), c, -m_new)) : 0.f;
+            const float p1 =
+                (c0 + 1 < valid) ? ex2_approx(fmaf(__uint_as_float(r[2 * i + 1]), c, -m_new)) : 0.f;
+            l_tile += p0 + p1;
+            pk[i] = pack_bf16x2(p0, p1);
+          }
         }
         // 32 columns = 4 chunks of 16 bytes; chunk index within the 64-key atom is XOR-swizzled with row&7
-        uint8_t* atom = prow + (c >> 1) * (BQ * 128);
+        uint8_t* atom = prow + (cc >> 1) * (BQ * 128);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          const int chunk = (c & 1) * 4 + q;
+          const int chunk = (cc & 1) * 4 + q;
           *reinterpret_cast<uint4*>(atom + ((chunk ^ (row & 7)) << 4)) =
               make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
         }
       }
-      l_run = l_run * a + l_tile;
+      l_run = fmaf(l_run, a, l_tile);
       m_run = m_new;
       // publish P_j: generic-proxy writes -> async proxy, TMEM reads of S_j ordered before the next MMA
       fence_proxy_async_smem();
       tc_fence_before();
-      mbar_arrive(smem_u32(&p_full[st]));
+      mbar_arrive(smem_u32(p_full));
       // fold in the previous tile's P.V while the tensor core works on this one
       if (j > 0) accumulate_o(j - 1, a_prev);
       a_prev = a;
     }
+    mbar_wait(smem_u32(&o_full[(T - 1) & 1]), ((T - 1) >> 1) & 1);
+    tc_fence_after();
     accumulate_o(T - 1, a_prev);
 
     if (q0 + row < p.q_len) {

@@ -5,7 +5,7 @@
 //   for q in 0..Q-1:  idx = argmin_k ||r - C_q[k]||^2 (first minimum wins);  r -= C_q[idx]
 //
 // The distance contraction runs on tcgen05 tensor cores in fp16 (fp32 accumulate) as a *filter*:
-//   s~_k = ||c_k||^2 - 2 r.c_k     with a rigorous bound |s~_k - s_k| <= E = 2 * 2^-9.5 * ||r|| * max_k ||c_k||
+//   s~_k = ||c_k||^2 - 2 r.c_k     with a rigorous bound |s~_k - s_k| <= E = 2 * 1.05 * 2^-10 * ||r|| * max_k ||c_k||
 // Every code whose approximate score is within 2E of the approximate minimum is a candidate; candidates
 // are re-scored exactly in fp64 from the fp32 operands, so the emitted index is the exact argmin
 // (ties -> lowest index) — bit-exact against the fp64 oracle — while >99% of the flops stay on tensor cores.
@@ -56,24 +56,25 @@ struct RvqDev {
   int Q, K;
 };
 
-// exact squared distance in fp64 between this thread's residual (column `rcol` of the transposed smem
-// tile, stride BF floats) and one fp32 codeword
+// exact squared distance in fp64 between one frame's residual (column `rcol` of the transposed smem tile,
+// stride BF floats) and one fp32 codeword.  Four independent accumulators (dims i mod 4) break the DFMA
+// dependency chain; the summation order is fixed, so equal inputs always give bit-equal results.
 __device__ __forceinline__ double exact_dist(const float* rcol, const float* __restrict__ c) {
-  double acc = 0.0;
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
   const float4* c4 = reinterpret_cast<const float4*>(c);
-#pragma unroll 4
+#pragma unroll 8
   for (int i = 0; i < rvq::D / 4; ++i) {
     const float4 v = __ldg(c4 + i);
     const double d0 = static_cast<double>(rcol[(4 * i + 0) * rvq::BF]) - static_cast<double>(v.x);
     const double d1 = static_cast<double>(rcol[(4 * i + 1) * rvq::BF]) - static_cast<double>(v.y);
     const double d2 = static_cast<double>(rcol[(4 * i + 2) * rvq::BF]) - static_cast<double>(v.z);
     const double d3 = static_cast<double>(rcol[(4 * i + 3) * rvq::BF]) - static_cast<double>(v.w);
-    acc = fma(d0, d0, acc);
-    acc = fma(d1, d1, acc);
-    acc = fma(d2, d2, acc);
-    acc = fma(d3, d3, acc);
+    a0 = fma(d0, d0, a0);
+    a1 = fma(d1, d1, a1);
+    a2 = fma(d2, d2, a2);
+    a3 = fma(d3, d3, a3);
   }
-  return acc;
+  return (a0 + a1) + (a2 + a3);
 }
 
 __global__ void __launch_bounds__(192, 1) rvq_encode_kernel(const __grid_constant__ RvqDev p) {
@@ -214,7 +215,7 @@ __global__ void __launch_bounds__(192, 1) rvq_encode_kernel(const __grid_constan
       const float cmax = __ldg(p.meta + 2 * q), cscale = __ldg(p.meta + 2 * q + 1);
       const float dscale = -2.0f * ldexpf(cscale, ex);  // s~ = cn2 + dscale * dot'
       // rigorous filter margin (see header comment); 1.001 covers the fp32 rounding of ||r|| itself
-      const float margin2 = 2.0f * (2.0f * 0.0013810679f /*2^-9.5*/ * sqrtf(ss) * 1.001f * cmax);
+      const float margin2 = 2.0f * (2.0f * 0.001026f /*1.05 * 2^-10*/ * sqrtf(ss) * 1.001f * cmax);
 
       // ---- scan all codes, keep the four best approximate scores ----
       float b0 = INFINITY, b1 = INFINITY, b2 = INFINITY, b3 = INFINITY;
@@ -249,27 +250,37 @@ __global__ void __launch_bounds__(192, 1) rvq_encode_kernel(const __grid_constan
       const float* cbq = p.codebooks + static_cast<long long>(q) * p.K * D;
       int best = i0;
       const float lim = b0 + margin2;
-      if (b1 <= lim) {
+      const bool overflow = b3 <= lim;  // more than three codes inside the uncertainty band
+      if (b1 <= lim && !overflow) {
         ++n_ambig;
-        double dbest;
-        if (b3 <= lim) {
-          // more than three codes inside the uncertainty band: exact scan of the whole codebook
-          ++n_full;
-          dbest = INFINITY;
-          best = 0;
-          for (int k = 0; k < p.K; ++k) {
-            const double dk = exact_dist(rcol, cbq + static_cast<long long>(k) * D);
-            if (dk < dbest) { dbest = dk; best = k; }
-          }
-        } else {
-          dbest = exact_dist(rcol, cbq + static_cast<long long>(i0) * D);
-          const double d1 = exact_dist(rcol, cbq + static_cast<long long>(i1) * D);
-          if (d1 < dbest || (d1 == dbest && i1 < best)) { dbest = d1; best = i1; }
-          if (b2 <= lim) {
-            const double d2 = exact_dist(rcol, cbq + static_cast<long long>(i2) * D);
-            if (d2 < dbest || (d2 == dbest && i2 < best)) { dbest = d2; best = i2; }
-          }
+        double dbest = exact_dist(rcol, cbq + static_cast<long long>(i0) * D);
+        const double d1 = exact_dist(rcol, cbq + static_cast<long long>(i1) * D);
+        if (d1 < dbest || (d1 == dbest && i1 < best)) { dbest = d1; best = i1; }
+        if (b2 <= lim) {
+          const double d2 = exact_dist(rcol, cbq + static_cast<long long>(i2) * D);
+          if (d2 < dbest || (d2 == dbest && i2 < best)) { dbest = d2; best = i2; }
         }
+      }
+      // overflow rows (rare): the whole warp scans the codebook exactly for that one row, 32 codes per lane
+      unsigned omask = __ballot_sync(0xffffffffu, overflow);
+      if (overflow) { ++n_ambig; ++n_full; }
+      while (omask) {
+        const int src = __ffs(omask) - 1;
+        omask &= omask - 1;
+        const float* rsrc = reinterpret_cast<const float*>(smem + OFF_R) + (warp * 32 + src);
+        double dmin = INFINITY;
+        int kmin = 0x7fffffff;
+        for (int k = lane; k < p.K; k += 32) {
+          const double dk = exact_dist(rsrc, cbq + static_cast<long long>(k) * D);
+          if (dk < dmin) { dmin = dk; kmin = k; }  // k ascending per lane: first minimum kept
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const double od = __shfl_xor_sync(0xffffffffu, dmin, o);
+          const int ok = __shfl_xor_sync(0xffffffffu, kmin, o);
+          if (od < dmin || (od == dmin && ok < kmin)) { dmin = od; kmin = ok; }
+        }
+        if (lane == src) best = kmin;
       }
       if (live) p.codes[f * p.Q + q] = best;
       // ---- residual update with the exact fp32 codeword (same op as the reference) ----
