@@ -1,9 +1,16 @@
 // Segmented tcgen05 GEMM for sm_100a with fused epilogues (see include/ns2_b200.h, section 1).
 //
-// One persistent CTA per SM, 256 threads, warp-specialised:
-//   warp 0     TMA producer: A tile (128 positions x 64 channels, 3-D map so that shifted rows of a causal
-//              conv that fall before position 0 are zero-filled by the TMA unit) + B tile (BN x 64)
-//   warp 1     tcgen05.mma issuer (one elected lane), accumulators in TMEM, double-buffered across tiles
+// Two kernels share the pipeline structure and the epilogue code:
+//   gemm2_kernel  CTA PAIRS (cluster of 2, tcgen05 cta_group::2): the pair owns a 256-position x BN tile; each CTA
+//                 stages its own 128 A rows and HALF of the B tile, so per-SM shared-memory traffic per MMA is halved
+//                 — the 1-CTA kernel is smem-bandwidth bound (operand reads + TMA fills ~ 192-256 B/clk vs 128 B/clk).
+//                 Used whenever a batch has more than 128 positions.
+//   gemm_kernel   single CTA, 128 x BN tile: the small-M problems (FiLM GEMM, perceiver, cross-attention K/V).
+// Both are persistent (one CTA per SM), 256 threads, warp-specialised:
+//   warp 0     TMA producer: A tile (128 positions x 64 channels, 3-D map so that shifted rows of a causal conv that
+//              fall before position 0 are zero-filled by the TMA unit) + B tile
+//   warp 1     tcgen05.mma issuer (one elected lane; leader CTA only in the pair kernel), accumulators in TMEM,
+//              double-buffered across tiles
 //   warp 2     TMEM allocator
 //   warps 4-7  epilogue: tcgen05.ld -> registers -> bias / residual / GEGLU / FiLM+gate -> global
 // Three pipelines: smem ring (full/empty mbarriers, TMA <-> MMA), TMEM double buffer (tmem_full/empty,
@@ -44,6 +51,183 @@ struct GemmDev {
   int film_gs;
 };
 
+struct TileCoord {
+  int g, b, n0, n_tile;
+};
+
+// ROWS = positions covered by one tile (128 for a single CTA, 256 for a CTA pair)
+template <int ROWS>
+__device__ __forceinline__ TileCoord decode_tile(const GemmDev& p, int tile) {
+  TileCoord t;
+  const int per_group = p.tiles_m * p.tiles_n;
+  t.g = tile / per_group;
+  const int r = tile - t.g * per_group;
+  const int m_tile = r / p.tiles_n;
+  t.n_tile = r - m_tile * p.tiles_n;
+  t.b = m_tile / p.tiles_per_batch;
+  t.n0 = (m_tile - t.b * p.tiles_per_batch) * ROWS;
+  return t;
+}
+
+// ------------------------------------------------------------------------------------------------
+// epilogue pieces (shared by both kernels)
+// ------------------------------------------------------------------------------------------------
+template <int W>
+__device__ __forceinline__ void tmem_load_f32(uint32_t taddr, float (&v)[W]) {
+  static_assert(W == 32 || W == 16, "chunk width");
+  if constexpr (W == 32) {
+    uint32_t r[32];
+    tmem_ld32(taddr, r);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+  } else {
+    uint32_t r[16];
+    tmem_ld16(taddr, r);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+  }
+}
+
+template <int W>
+__device__ __forceinline__ void add_vec(float (&v)[W], const float* __restrict__ src) {
+  const float4* s4 = reinterpret_cast<const float4*>(src);
+#pragma unroll
+  for (int i = 0; i < W / 4; ++i) {
+    const float4 b4 = __ldg(s4 + i);
+    v[4 * i + 0] += b4.x;
+    v[4 * i + 1] += b4.y;
+    v[4 * i + 2] += b4.z;
+    v[4 * i + 3] += b4.w;
+  }
+}
+
+template <int W>
+__device__ __forceinline__ void store_bf16(const float (&v)[W], __nv_bfloat16* dst) {
+  uint4* o4 = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+  for (int i = 0; i < W / 8; ++i) {
+    uint4 w;
+    w.x = pack_bf16x2(v[8 * i + 0], v[8 * i + 1]);
+    w.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
+    w.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]);
+    w.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
+    o4[i] = w;
+  }
+}
+
+template <int W>
+__device__ __forceinline__ void store_f32(const float (&v)[W], float* dst) {
+  float4* o4 = reinterpret_cast<float4*>(dst);
+#pragma unroll
+  for (int i = 0; i < W / 4; ++i)
+    o4[i] = make_float4(v[4 * i + 0], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+}
+
+// one chunk of W accumulator columns starting at tile column `tc` of the BF16 / F32 epilogues
+template <int W, int EPI>
+__device__ __forceinline__ void epi_plain_chunk(const GemmDev& p, const TileCoord& t, int tile_col0, int tc,
+                                                uint32_t taddr, bool row_ok, long long grow) {
+  const int col0 = tile_col0 + tc;
+  float v[W];
+  tmem_load_f32<W>(taddr + tc, v);
+  if (p.bias != nullptr) add_vec<W>(v, p.bias + t.g * p.b_grs + col0);
+  if (!row_ok) return;
+  if constexpr (EPI == NS2_EPI_BF16) {
+    store_bf16<W>(v, reinterpret_cast<__nv_bfloat16*>(p.out) + grow * p.out_rs + t.g * p.out_gcs + col0);
+  } else {
+    if (p.resid != nullptr) add_vec<W>(v, p.resid + grow * p.resid_rs + t.g * p.out_gcs + col0);
+    store_f32<W>(v, reinterpret_cast<float*>(p.out) + grow * p.out_rs + t.g * p.out_gcs + col0);
+  }
+}
+
+// Full epilogue of one 128-row x BN accumulator tile held in this CTA's TMEM.
+//   taddr: TMEM address of (first lane of this warp, first column of the accumulator stage)
+//   npos : position (row inside the batch) owned by this thread
+template <int BN, int NACC, int EPI>
+__device__ __forceinline__ void epilogue_tile(const GemmDev& p, const TileCoord& t, uint32_t taddr, int npos) {
+  const bool row_ok = npos < p.a_rows;
+  const long long grow = static_cast<long long>(t.b) * p.a_rows + npos;
+  const int tile_col0 = t.n_tile * BN;
+  if constexpr (EPI == NS2_EPI_BF16 || EPI == NS2_EPI_F32) {
+#pragma unroll 1
+    for (int tc = 0; tc + 32 <= BN; tc += 32) {
+      if (tile_col0 + tc >= p.n) break;
+      epi_plain_chunk<32, EPI>(p, t, tile_col0, tc, taddr, row_ok, grow);
+    }
+    if constexpr (BN % 32 != 0) {
+      constexpr int tc = BN - 16;
+      if (tile_col0 + tc < p.n) epi_plain_chunk<16, EPI>(p, t, tile_col0, tc, taddr, row_ok, grow);
+    }
+  } else if constexpr (EPI == NS2_EPI_GEGLU) {
+    static_assert(EPI != NS2_EPI_GEGLU || BN == 256, "GEGLU tiles pair 128 value + 128 gate rows");
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      const int pcol0 = tile_col0 + c * 32;  // packed (value) column
+      if (pcol0 >= p.n) break;
+      float xv[32], gv[32];
+      {
+        uint32_t rv[32], rg[32];
+        tmem_ld32(taddr + c * 32, rv);
+        tmem_ld32(taddr + 128 + c * 32, rg);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          xv[i] = __uint_as_float(rv[i]);
+          gv[i] = __uint_as_float(rg[i]);
+        }
+      }
+      add_vec<32>(xv, p.bias + t.g * p.b_grs + pcol0);
+      add_vec<32>(gv, p.bias + t.g * p.b_grs + pcol0 + 128);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) xv[i] *= gelu_erf(gv[i]);
+      if (row_ok)
+        store_bf16<32>(xv, reinterpret_cast<__nv_bfloat16*>(p.out) + grow * p.out_rs + t.g * p.out_gcs +
+                               t.n_tile * 128 + c * 32);
+    }
+  } else {  // NS2_EPI_WAVENET
+    static_assert(EPI != NS2_EPI_WAVENET || NACC == 2, "wavenet block needs conv + res accumulators");
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      const int col0 = tile_col0 + c * 32;
+      if (col0 >= p.n) break;
+      float y[32], rr[32];
+      {
+        uint32_t rc[32], r1[32];
+        tmem_ld32(taddr + c * 32, rc);
+        tmem_ld32(taddr + BN + c * 32, r1);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          y[i] = __uint_as_float(rc[i]);
+          rr[i] = __uint_as_float(r1[i]);
+        }
+      }
+      const float* b0 = p.bias + t.g * p.b_grs + col0;
+      add_vec<32>(y, b0);
+      add_vec<32>(rr, b0 + p.bias1_off);
+      const float4* gm = reinterpret_cast<const float4*>(p.film + t.b * p.film_bs + t.g * p.film_gs + col0);
+      const float4* bt = reinterpret_cast<const float4*>(p.film + t.b * p.film_bs + t.g * p.film_gs + col0 + p.n);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float4 g4 = __ldg(gm + i), b4 = __ldg(bt + i);
+        const float ga[4] = {g4.x, g4.y, g4.z, g4.w}, be[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float z = fmaf(y[4 * i + j], ga[j], be[j]);
+          y[4 * i + j] = tanhf(z) * sigmoid_f(z) + rr[4 * i + j];
+        }
+      }
+      if (row_ok)
+        store_bf16<32>(y, reinterpret_cast<__nv_bfloat16*>(p.out) + grow * p.out_rs + t.g * p.out_gcs + col0);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// single-CTA kernel
+// ------------------------------------------------------------------------------------------------
 template <int BN, int NACC>
 struct GemmCfg {
   static constexpr int A_BYTES = BM * BK * 2;
@@ -55,22 +239,6 @@ struct GemmCfg {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
-struct TileCoord {
-  int g, b, n0, n_tile;
-};
-
-__device__ __forceinline__ TileCoord decode_tile(const GemmDev& p, int tile) {
-  TileCoord t;
-  const int per_group = p.tiles_m * p.tiles_n;
-  t.g = tile / per_group;
-  const int r = tile - t.g * per_group;
-  const int m_tile = r / p.tiles_n;
-  t.n_tile = r - m_tile * p.tiles_n;
-  t.b = m_tile / p.tiles_per_batch;
-  t.n0 = (m_tile - t.b * p.tiles_per_batch) * BM;
-  return t;
-}
-
 template <int BN, int NACC, int EPI>
 __global__ void __launch_bounds__(256, 1) gemm_kernel(const __grid_constant__ GemmDev p) {
   using Cfg = GemmCfg<BN, NACC>;
@@ -78,9 +246,9 @@ __global__ void __launch_bounds__(256, 1) gemm_kernel(const __grid_constant__ Ge
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
-  uint64_t* full_bar = bars;                       // [STAGES]
-  uint64_t* empty_bar = bars + Cfg::STAGES;        // [STAGES]
-  uint64_t* tfull_bar = bars + 2 * Cfg::STAGES;    // [2]
+  uint64_t* full_bar = bars;                          // [STAGES]
+  uint64_t* empty_bar = bars + Cfg::STAGES;           // [STAGES]
+  uint64_t* tfull_bar = bars + 2 * Cfg::STAGES;       // [2]
   uint64_t* tempty_bar = bars + 2 * Cfg::STAGES + 2;  // [2]
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::STAGES + 4);
 
@@ -113,7 +281,7 @@ __global__ void __launch_bounds__(256, 1) gemm_kernel(const __grid_constant__ Ge
     if (lane == 0) {
       uint32_t it = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        const TileCoord t = decode_tile(p, tile);
+        const TileCoord t = decode_tile<BM>(p, tile);
         const int dil = p.dil[t.g];
         for (int s = 0; s < p.num_segs; ++s) {
           const ns2_gemm_seg sg = p.segs[s];
@@ -173,145 +341,15 @@ __global__ void __launch_bounds__(256, 1) gemm_kernel(const __grid_constant__ Ge
   } else if (warp >= 4) {
     // =============================== epilogue ===================================
     const int ew = warp - 4;  // == warp % 4: the TMEM lane quarter this warp may read
-    const int row = ew * 32 + lane;
     uint32_t ti = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++ti) {
-      const TileCoord t = decode_tile(p, tile);
+      const TileCoord t = decode_tile<BM>(p, tile);
       const uint32_t as = ti & 1;
       const uint32_t aphase = (ti >> 1) & 1;
       mbar_wait(smem_u32(&tfull_bar[as]), aphase);
       tc_fence_after();
-      const int npos = t.n0 + row;
-      const bool row_ok = npos < p.a_rows;
-      const long long grow = static_cast<long long>(t.b) * p.a_rows + npos;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + as * Cfg::ACC_COLS;
-
-      if constexpr (EPI == NS2_EPI_BF16 || EPI == NS2_EPI_F32) {
-#pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
-          const int col0 = t.n_tile * BN + c * 32;
-          if (col0 >= p.n) break;
-          uint32_t r[32];
-          tmem_ld32(taddr + c * 32, r);
-          tmem_ld_wait();
-          float v[32];
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-          if (p.bias != nullptr) {
-            const float4* bp = reinterpret_cast<const float4*>(p.bias + t.g * p.b_grs + col0);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float4 b4 = __ldg(bp + i);
-              v[4 * i + 0] += b4.x;
-              v[4 * i + 1] += b4.y;
-              v[4 * i + 2] += b4.z;
-              v[4 * i + 3] += b4.w;
-            }
-          }
-          if (row_ok) {
-            if constexpr (EPI == NS2_EPI_BF16) {
-              __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + grow * p.out_rs +
-                                  t.g * p.out_gcs + col0;
-              uint4* o4 = reinterpret_cast<uint4*>(op);
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                uint4 w;
-                w.x = pack_bf16x2(v[8 * i + 0], v[8 * i + 1]);
-                w.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
-                w.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]);
-                w.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
-                o4[i] = w;
-              }
-            } else {
-              if (p.resid != nullptr) {
-                const float4* rp = reinterpret_cast<const float4*>(p.resid + grow * p.resid_rs +
-                                                                   t.g * p.out_gcs + col0);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                  const float4 r4 = __ldg(rp + i);
-                  v[4 * i + 0] += r4.x;
-                  v[4 * i + 1] += r4.y;
-                  v[4 * i + 2] += r4.z;
-                  v[4 * i + 3] += r4.w;
-                }
-              }
-              float4* o4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) +
-                                                     grow * p.out_rs + t.g * p.out_gcs + col0);
-#pragma unroll
-              for (int i = 0; i < 8; ++i)
-                o4[i] = make_float4(v[4 * i + 0], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-            }
-          }
-        }
-      } else if constexpr (EPI == NS2_EPI_GEGLU) {
-        static_assert(EPI != NS2_EPI_GEGLU || BN == 256, "GEGLU tiles pair 128 value + 128 gate rows");
-#pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-          const int pcol0 = t.n_tile * BN + c * 32;  // packed (value) column
-          if (pcol0 >= p.n) break;
-          uint32_t rv[32], rg[32];
-          tmem_ld32(taddr + c * 32, rv);
-          tmem_ld32(taddr + 128 + c * 32, rg);
-          tmem_ld_wait();
-          const float* bv = p.bias + t.g * p.b_grs + pcol0;
-          const float* bg = bv + 128;
-          uint32_t packed[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float x0 = __uint_as_float(rv[2 * i]) + __ldg(bv + 2 * i);
-            const float x1 = __uint_as_float(rv[2 * i + 1]) + __ldg(bv + 2 * i + 1);
-            const float g0 = __uint_as_float(rg[2 * i]) + __ldg(bg + 2 * i);
-            const float g1 = __uint_as_float(rg[2 * i + 1]) + __ldg(bg + 2 * i + 1);
-            packed[i] = pack_bf16x2(gelu_erf(g0) * x0, gelu_erf(g1) * x1);
-          }
-          if (row_ok) {
-            const int ocol0 = t.n_tile * 128 + c * 32;
-            uint4* o4 = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) +
-                                                 grow * p.out_rs + t.g * p.out_gcs + ocol0);
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-              o4[i] = make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2],
-                                 packed[4 * i + 3]);
-          }
-        }
-      } else {  // NS2_EPI_WAVENET
-        static_assert(EPI != NS2_EPI_WAVENET || NACC == 2, "wavenet block needs conv + res accumulators");
-#pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
-          const int col0 = t.n_tile * BN + c * 32;
-          if (col0 >= p.n) break;
-          uint32_t rc[32], rr[32];
-          tmem_ld32(taddr + c * 32, rc);
-          tmem_ld32(taddr + BN + c * 32, rr);
-          tmem_ld_wait();
-          const float* b0 = p.bias + t.g * p.b_grs + col0;
-          const float* b1 = b0 + p.bias1_off;
-          const float* gm = p.film + t.b * p.film_bs + t.g * p.film_gs + col0;
-          const float* bt = gm + p.n;
-          uint32_t packed[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            float o[2];
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-              const int e = 2 * i + j;
-              float y = __uint_as_float(rc[e]) + __ldg(b0 + e);
-              y = y * __ldg(gm + e) + __ldg(bt + e);
-              const float gated = tanhf(y) * sigmoid_f(y);
-              o[j] = gated + __uint_as_float(rr[e]) + __ldg(b1 + e);
-            }
-            packed[i] = pack_bf16x2(o[0], o[1]);
-          }
-          if (row_ok) {
-            uint4* o4 = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) +
-                                                 grow * p.out_rs + t.g * p.out_gcs + col0);
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-              o4[i] = make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2],
-                                 packed[4 * i + 3]);
-          }
-        }
-      }
+      epilogue_tile<BN, NACC, EPI>(p, t, taddr, t.n0 + ew * 32 + lane);
       // release this accumulator stage back to the MMA warp
       tc_fence_before();
       __syncwarp();
@@ -327,6 +365,159 @@ __global__ void __launch_bounds__(256, 1) gemm_kernel(const __grid_constant__ Ge
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// CTA-pair kernel (cluster of 2, cta_group::2)
+// ------------------------------------------------------------------------------------------------
+template <int BN, int NACC>
+struct Gemm2Cfg {
+  static constexpr int A_BYTES = BM * BK * 2;            // this CTA's 128 rows
+  static constexpr int B_BYTES = (BN / 2) * BK * 2;      // this CTA's half of the B tile
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;  // multiple of 1024 for BN in {128, 176, 256}
+  static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 8 ? 8 : (200 * 1024) / STAGE_BYTES;
+  static constexpr int ACC_COLS = BN * NACC;
+  static constexpr int ACC_STRIDE = (ACC_COLS <= 128) ? 128 : 256;  // column offset of the second stage
+  static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+  static_assert(STAGE_BYTES % 1024 == 0, "stage must keep 1024-byte alignment of the swizzled tiles");
+  static_assert(ACC_COLS <= 256, "accumulators of one stage must fit 256 TMEM columns");
+};
+
+template <int BN, int NACC, int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
+    gemm2_kernel(const __grid_constant__ GemmDev p) {
+  using Cfg = Gemm2Cfg<BN, NACC>;
+  extern __shared__ uint8_t smem_raw[];
+  // identical carve-up in both CTAs of the pair (the dynamic smem base offset is the same for every CTA of a launch)
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint64_t* full_bar = bars;                          // [STAGES]  used in the leader CTA only
+  uint64_t* empty_bar = bars + Cfg::STAGES;           // [STAGES]  one per CTA, signalled by multicast commit
+  uint64_t* tfull_bar = bars + 2 * Cfg::STAGES;       // [2]       one per CTA, multicast commit
+  uint64_t* tempty_bar = bars + 2 * Cfg::STAGES + 2;  // [2]       leader only: 8 arrivals (4 warps x 2 CTAs)
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int pair = blockIdx.x >> 1;
+  const int num_pairs = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmA);
+    tma_prefetch_desc(&p.tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < Cfg::STAGES; ++i) {
+      mbar_init(smem_u32(&full_bar[i]), 1);
+      mbar_init(smem_u32(&empty_bar[i]), 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(&tfull_bar[i]), 1);
+      mbar_init(smem_u32(&tempty_bar[i]), 8);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc_2cta(smem_u32(tmem_holder), Cfg::TMEM_COLS);
+  tc_fence_before();
+  __syncwarp();
+  cluster_sync_all();  // barriers of BOTH CTAs are initialised before any remote arrive / TMA signal
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  if (warp == 0) {
+    // =============================== TMA producer (both CTAs) ===================
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = pair; tile < p.num_tiles; tile += num_pairs) {
+        const TileCoord t = decode_tile<2 * BM>(p, tile);
+        const int dil = p.dil[t.g];
+        for (int s = 0; s < p.num_segs; ++s) {
+          const ns2_gemm_seg sg = p.segs[s];
+          const int row0 = t.n0 + static_cast<int>(rank) * BM - sg.shift_units * dil;
+          const int a_c0 = t.g * p.a_gcs + sg.a_col_off;
+          const int b_r0 = t.g * p.b_grs + t.n_tile * BN + static_cast<int>(rank) * (BN / 2);
+          const int kblocks = (sg.k_len + BK - 1) / BK;
+          for (int kb = 0; kb < kblocks; ++kb, ++it) {
+            const uint32_t stage = it % Cfg::STAGES;
+            const uint32_t phase = (it / Cfg::STAGES) & 1;
+            mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+            // the transaction bytes of both CTAs are counted on the leader's barrier
+            const uint32_t fb_leader = mapa_shared(smem_u32(&full_bar[stage]), 0);
+            if (leader) mbar_arrive_expect_tx(smem_u32(&full_bar[stage]), 2 * Cfg::STAGE_BYTES);
+            uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+            tma_load_3d_2sm(smem_u32(sa), &p.tmA, fb_leader, a_c0 + kb * BK, row0, t.b);
+            tma_load_2d_2sm(smem_u32(sa + Cfg::A_BYTES), &p.tmB, fb_leader, sg.b_col_off + kb * BK, b_r0);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer (leader CTA only) ================
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_f16(2 * BM, BN, /*bf16*/ 1, 0, 0);
+      uint32_t it = 0;
+      uint32_t ti = 0;
+      for (int tile = pair; tile < p.num_tiles; tile += num_pairs, ++ti) {
+        const uint32_t as = ti & 1;
+        const uint32_t aphase = (ti >> 1) & 1;
+        mbar_wait(smem_u32(&tempty_bar[as]), aphase ^ 1);
+        tc_fence_after();
+        uint32_t started = 0;
+        for (int s = 0; s < p.num_segs; ++s) {
+          const int acc = p.segs[s].acc;
+          const uint32_t d_tmem = tmem_base + as * Cfg::ACC_STRIDE + acc * BN;
+          const int kblocks = (p.segs[s].k_len + BK - 1) / BK;
+          for (int kb = 0; kb < kblocks; ++kb, ++it) {
+            const uint32_t stage = it % Cfg::STAGES;
+            const uint32_t phase = (it / Cfg::STAGES) & 1;
+            mbar_wait(smem_u32(&full_bar[stage]), phase);
+            tc_fence_after();
+            const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+            const uint64_t da = umma_desc_sw128(sa, 16, 1024);
+            const uint64_t db = umma_desc_sw128(sa + Cfg::A_BYTES, 16, 1024);
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k)
+              tc_mma_f16_2cta(d_tmem, da + 2 * k, db + 2 * k, idesc, ((started >> acc) & 1) | (k > 0));
+            started |= 1u << acc;
+            tc_commit_2cta(smem_u32(&empty_bar[stage]), 0b11);  // frees the slot in both CTAs
+          }
+        }
+        tc_commit_2cta(smem_u32(&tfull_bar[as]), 0b11);  // both CTAs' epilogues may read their 128 rows
+      }
+    }
+  } else if (warp >= 4) {
+    // =============================== epilogue (both CTAs) =======================
+    const int ew = warp - 4;
+    uint32_t ti = 0;
+    for (int tile = pair; tile < p.num_tiles; tile += num_pairs, ++ti) {
+      const TileCoord t = decode_tile<2 * BM>(p, tile);
+      const uint32_t as = ti & 1;
+      const uint32_t aphase = (ti >> 1) & 1;
+      mbar_wait(smem_u32(&tfull_bar[as]), aphase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + as * Cfg::ACC_STRIDE;
+      epilogue_tile<BN, NACC, EPI>(p, t, taddr, t.n0 + static_cast<int>(rank) * BM + ew * 32 + lane);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(&tempty_bar[as]), 0));
+    }
+  }
+
+  // neither CTA may free TMEM / exit while its peer can still touch it (MMA writes, remote barrier arrives)
+  tc_fence_before();
+  __syncwarp();  // the cluster barrier is .aligned: every warp must be converged when it executes it
+  cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_2cta(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
 template <int BN, int NACC, int EPI>
 static int launch_gemm(const GemmDev& dev, cudaStream_t stream) {
   using Cfg = GemmCfg<BN, NACC>;
@@ -339,6 +530,24 @@ static int launch_gemm(const GemmDev& dev, cudaStream_t stream) {
   }
   const int grid = dev.num_tiles < num_sms() ? dev.num_tiles : num_sms();
   kern<<<grid, 256, Cfg::SMEM_BYTES, stream>>>(dev);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  NS2_CUDA_CHECK(cudaGetLastError());
+  return kOk;
+}
+
+template <int BN, int NACC, int EPI>
+static int launch_gemm2(const GemmDev& dev, cudaStream_t stream) {
+  using Cfg = Gemm2Cfg<BN, NACC>;
+  static bool configured = false;
+  auto kern = gemm2_kernel<BN, NACC, EPI>;
+  if (!configured) {
+    NS2_CUDA_CHECK(
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    configured = true;
+  }
+  int pairs = num_sms() / 2;
+  if (dev.num_tiles < pairs) pairs = dev.num_tiles;
+  kern<<<2 * pairs, 256, Cfg::SMEM_BYTES, stream>>>(dev);  // __cluster_dims__(2,1,1)
   g_launches.fetch_add(1, std::memory_order_relaxed);
   NS2_CUDA_CHECK(cudaGetLastError());
   return kOk;
@@ -364,9 +573,7 @@ extern "C" int ns2_gemm(const ns2_gemm_args* a, ns2_stream_t stream_) {
     NS2_REQUIRE(sg.k_len > 0 && sg.acc >= 0 && sg.acc <= 1 && sg.shift_units >= 0,
                 "ns2_gemm: bad segment %d", s);
     const bool ends_at_edge = (sg.b_col_off + sg.k_len == a->b_cols) &&
-                              ((a->groups - 1) * a->a_group_col_stride + sg.a_col_off + sg.k_len ==
-                               a->a_cols) &&
-                              a->groups == 1;
+                              (sg.a_col_off + sg.k_len == a->a_cols) && a->groups == 1;
     NS2_REQUIRE(sg.k_len % BK == 0 || ends_at_edge,
                 "ns2_gemm: segment %d k_len=%d is not a multiple of 64 and does not end at the edge", s,
                 sg.k_len);
@@ -374,7 +581,9 @@ extern "C" int ns2_gemm(const ns2_gemm_args* a, ns2_stream_t stream_) {
                 "ns2_gemm: second accumulator only exists for the WAVENET epilogue");
   }
   if (a->epilogue == NS2_EPI_WAVENET)
-    NS2_REQUIRE(a->film != nullptr && a->bias != nullptr, "ns2_gemm: WAVENET needs film and bias");
+    NS2_REQUIRE(a->film != nullptr && a->bias != nullptr && a->film_batch_stride % 4 == 0 &&
+                    a->film_group_stride % 4 == 0 && (reinterpret_cast<uintptr_t>(a->film) & 15) == 0,
+                "ns2_gemm: WAVENET needs bias and a 16-byte aligned film table");
   if (a->epilogue == NS2_EPI_GEGLU)
     NS2_REQUIRE(a->bias != nullptr && a->n % 256 == 0,
                 "ns2_gemm: GEGLU needs bias and n %% 256 == 0 (n=%d)", a->n);
@@ -385,6 +594,18 @@ extern "C" int ns2_gemm(const ns2_gemm_args* a, ns2_stream_t stream_) {
   NS2_REQUIRE(a->out_row_stride % 8 == 0 && a->out_group_col_stride % 8 == 0 &&
                   (reinterpret_cast<uintptr_t>(a->out) & 15) == 0,
               "ns2_gemm: out must be 16-byte aligned with strides multiple of 8");
+  if (a->resid != nullptr)
+    NS2_REQUIRE(a->resid_row_stride % 4 == 0 && (reinterpret_cast<uintptr_t>(a->resid) & 15) == 0,
+                "ns2_gemm: resid must be 16-byte aligned");
+
+  // ---- kernel / tile selection ----
+  const bool pair = a->a_rows > BM;  // CTA pairs need > 128 positions per batch to fill both halves
+  int bn;
+  if (a->epilogue == NS2_EPI_WAVENET) bn = 128;
+  else if (a->epilogue == NS2_EPI_GEGLU) bn = 256;
+  else if (pair) bn = (a->n % 256 == 0) ? 256 : (a->n % 176 == 0 ? 176 : (a->n >= 1024 ? 256 : 128));
+  else bn = (a->n % 256 == 0 && a->n >= 1024) ? 256 : 128;
+  const int tile_rows = pair ? 2 * BM : BM;
 
   GemmDev dev;
   memset(&dev, 0, sizeof(dev));
@@ -395,19 +616,15 @@ extern "C" int ns2_gemm(const ns2_gemm_args* a, ns2_stream_t stream_) {
     int rc = make_tmap_16bit(&dev.tmA, a->A, 3, dims, strides, box);
     if (rc != kOk) return rc;
   }
-  const int bn = (a->epilogue == NS2_EPI_WAVENET) ? 128
-                 : (a->epilogue == NS2_EPI_GEGLU) ? 256
-                 : (a->n % 256 == 0 && a->n >= 1024) ? 256
-                                                     : 128;
   {
     const uint64_t dims[2] = {(uint64_t)a->b_cols, (uint64_t)a->b_rows};
     const uint64_t strides[2] = {2, (uint64_t)a->b_row_stride * 2};
-    const uint32_t box[2] = {BK, (uint32_t)bn};
+    const uint32_t box[2] = {BK, (uint32_t)(pair ? bn / 2 : bn)};
     int rc = make_tmap_16bit(&dev.tmB, a->B, 2, dims, strides, box);
     if (rc != kOk) return rc;
   }
   dev.tiles_n = (a->n + bn - 1) / bn;
-  dev.tiles_per_batch = (a->a_rows + BM - 1) / BM;
+  dev.tiles_per_batch = (a->a_rows + tile_rows - 1) / tile_rows;
   dev.tiles_m = dev.tiles_per_batch * a->a_batches;
   dev.num_tiles = dev.tiles_m * dev.tiles_n * a->groups;
   dev.a_rows = a->a_rows;
@@ -429,6 +646,24 @@ extern "C" int ns2_gemm(const ns2_gemm_args* a, ns2_stream_t stream_) {
   dev.film_bs = a->film_batch_stride;
   dev.film_gs = a->film_group_stride;
 
+  if (pair) {
+    switch (a->epilogue) {
+      case NS2_EPI_BF16:
+        return bn == 256   ? launch_gemm2<256, 1, NS2_EPI_BF16>(dev, stream)
+               : bn == 176 ? launch_gemm2<176, 1, NS2_EPI_BF16>(dev, stream)
+                           : launch_gemm2<128, 1, NS2_EPI_BF16>(dev, stream);
+      case NS2_EPI_F32:
+        return bn == 256   ? launch_gemm2<256, 1, NS2_EPI_F32>(dev, stream)
+               : bn == 176 ? launch_gemm2<176, 1, NS2_EPI_F32>(dev, stream)
+                           : launch_gemm2<128, 1, NS2_EPI_F32>(dev, stream);
+      case NS2_EPI_GEGLU:
+        return launch_gemm2<256, 1, NS2_EPI_GEGLU>(dev, stream);
+      case NS2_EPI_WAVENET:
+        return launch_gemm2<128, 2, NS2_EPI_WAVENET>(dev, stream);
+      default:
+        return set_error(kErrInvalidArg, "ns2_gemm: unknown epilogue %d", a->epilogue);
+    }
+  }
   switch (a->epilogue) {
     case NS2_EPI_BF16:
       return bn == 256 ? launch_gemm<256, 1, NS2_EPI_BF16>(dev, stream)
