@@ -23,6 +23,7 @@
 #include "../../include/ns2_b200.h"
 
 #include <atomic>
+#include <stdlib.h>
 
 namespace ns2 {
 
@@ -34,6 +35,8 @@ constexpr int BK = 64;
 struct GemmDev {
   CUtensorMap tmA;
   CUtensorMap tmB;
+  CUtensorMap tmOut;   // pair kernel: TMA store / reduce-add target (3-D: columns, positions, batch)
+  int reduce_add;      // pair kernel, F32 epilogue with resid == out: out += acc + bias via TMA reduce-add
   int tiles_n, tiles_per_batch, tiles_m, num_tiles;
   int a_rows, n, groups;
   int a_gcs, b_grs, out_gcs;
@@ -49,7 +52,14 @@ struct GemmDev {
   const float* film;
   long long film_bs;
   int film_gs;
+  int debug;  // NS2_GEMM_DEBUG bits (bring-up only): 1 = skip global stores, 2 = skip TMEM loads, 4 = skip epilogue
 };
+
+__device__ long long g_gemm_dbg[16 * 64];  // bring-up timeline: [tile][slot] clock64 stamps of pair 0 (NS2_GEMM_DEBUG & 8)
+#define NS2_DBG_STAMP(slot)                                                             \
+  do {                                                                                \
+    if ((p.debug & 8) && pair == 0 && leader && ti < 64) g_gemm_dbg[ti * 16 + (slot)] = clock64(); \
+  } while (0)
 
 struct TileCoord {
   int g, b, n0, n_tile;
@@ -131,7 +141,13 @@ __device__ __forceinline__ void epi_plain_chunk(const GemmDev& p, const TileCoor
                                                 uint32_t taddr, bool row_ok, long long grow) {
   const int col0 = tile_col0 + tc;
   float v[W];
-  tmem_load_f32<W>(taddr + tc, v);
+  if (p.debug & 2) {
+#pragma unroll
+    for (int i = 0; i < W; ++i) v[i] = 1.0f;
+  } else {
+    tmem_load_f32<W>(taddr + tc, v);
+  }
+  if (p.debug & 1) row_ok = row_ok && (v[0] == 123456.0f);
   if (p.bias != nullptr) add_vec<W>(v, p.bias + t.g * p.b_grs + col0);
   if (!row_ok) return;
   if constexpr (EPI == NS2_EPI_BF16) {
@@ -221,6 +237,159 @@ __device__ __forceinline__ void epilogue_tile(const GemmDev& p, const TileCoord&
       }
       if (row_ok)
         store_bf16<32>(y, reinterpret_cast<__nv_bfloat16*>(p.out) + grow * p.out_rs + t.g * p.out_gcs + col0);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// pair-kernel epilogue: registers -> 128B-swizzled smem staging (per warp, double-buffered) -> TMA store.
+// Per-thread scattered 16-byte global stores (the single-CTA epilogue above) cost ~10k cycles per 128x256 tile
+// in the LSU; the bulk stores are issued by one lane per warp and overlap with the next chunk's math.
+// ------------------------------------------------------------------------------------------------
+constexpr int STG_BYTES = 32 * 128;  // one box: 32 rows x 128 bytes
+
+struct Stager {
+  uint32_t base;      // smem address of this warp's two staging boxes
+  uint32_t count;     // boxes issued so far
+  int lane;
+  __device__ __forceinline__ uint32_t acquire() {
+    // the box used two stores ago must have been read out by the TMA engine
+    if (lane == 0) tma_store_wait_read<1>();
+    __syncwarp();
+    return base + (count & 1) * STG_BYTES;
+  }
+  // thread writes 16-byte piece j (0..7) of its 128-byte row
+  __device__ __forceinline__ void put(uint32_t box, int j, uint4 v) const {
+    const uint32_t addr = box + lane * 128 + ((j ^ (lane & 7)) << 4);
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+                 : "memory");
+  }
+  __device__ __forceinline__ void submit(const CUtensorMap* m, uint32_t box, int c0, int c1, int c2, bool reduce) {
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      if (reduce) tma_reduce_add_3d(m, box, c0, c1, c2);
+      else tma_store_3d(m, box, c0, c1, c2);
+      tma_store_commit();
+    }
+    ++count;
+  }
+};
+
+__device__ __forceinline__ void put_bf16x32(const Stager& st, uint32_t box, int half, const float (&v)[32]) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    uint4 w;
+    w.x = pack_bf16x2(v[8 * q + 0], v[8 * q + 1]);
+    w.y = pack_bf16x2(v[8 * q + 2], v[8 * q + 3]);
+    w.z = pack_bf16x2(v[8 * q + 4], v[8 * q + 5]);
+    w.w = pack_bf16x2(v[8 * q + 6], v[8 * q + 7]);
+    st.put(box, half * 4 + q, w);
+  }
+}
+
+// taddr: TMEM address (first lane of this warp, first column of the accumulator stage); row0: first position of
+// this warp's 32 rows.  Returns after the last TMEM read of the tile (stores may still be in flight).
+template <int BN, int NACC, int EPI>
+__device__ __forceinline__ void epilogue_tile_tma(const GemmDev& p, const TileCoord& t, uint32_t taddr, int row0,
+                                                  Stager& st) {
+  const int tile_col0 = t.n_tile * BN;
+  if constexpr (EPI == NS2_EPI_BF16) {
+#pragma unroll 1
+    for (int oc = 0; oc < BN; oc += 64) {
+      if (tile_col0 + oc >= p.n) break;
+      const uint32_t box = st.acquire();
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        float v[32];
+        tmem_load_f32<32>(taddr + oc + h * 32, v);
+        if (p.bias != nullptr) add_vec<32>(v, p.bias + t.g * p.b_grs + tile_col0 + oc + h * 32);
+        put_bf16x32(st, box, h, v);
+      }
+      st.submit(&p.tmOut, box, t.g * p.out_gcs + tile_col0 + oc, row0, t.b, false);
+    }
+  } else if constexpr (EPI == NS2_EPI_F32) {
+#pragma unroll 1
+    for (int oc = 0; oc < BN; oc += 32) {
+      if (tile_col0 + oc >= p.n) break;
+      const uint32_t box = st.acquire();
+      float v[32];
+      tmem_load_f32<32>(taddr + oc, v);
+      if (p.bias != nullptr) add_vec<32>(v, p.bias + t.g * p.b_grs + tile_col0 + oc);
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        st.put(box, q, make_uint4(__float_as_uint(v[4 * q]), __float_as_uint(v[4 * q + 1]),
+                                  __float_as_uint(v[4 * q + 2]), __float_as_uint(v[4 * q + 3])));
+      st.submit(&p.tmOut, box, t.g * p.out_gcs + tile_col0 + oc, row0, t.b, p.reduce_add != 0);
+    }
+  } else if constexpr (EPI == NS2_EPI_GEGLU) {
+    static_assert(EPI != NS2_EPI_GEGLU || BN == 256, "GEGLU tiles pair 128 value + 128 gate rows");
+#pragma unroll 1
+    for (int oc = 0; oc < 128; oc += 64) {  // output columns of this tile
+      const uint32_t box = st.acquire();
+#pragma unroll 1
+      for (int h = 0; h < 2; ++h) {
+        const int c = oc + h * 32;
+        float xv[32], gv[32];
+        {
+          uint32_t rv[32], rg[32];
+          tmem_ld32(taddr + c, rv);
+          tmem_ld32(taddr + 128 + c, rg);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            xv[i] = __uint_as_float(rv[i]);
+            gv[i] = __uint_as_float(rg[i]);
+          }
+        }
+        add_vec<32>(xv, p.bias + t.g * p.b_grs + tile_col0 + c);
+        add_vec<32>(gv, p.bias + t.g * p.b_grs + tile_col0 + c + 128);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) xv[i] *= gelu_erf_fast(gv[i]);
+        put_bf16x32(st, box, h, xv);
+      }
+      st.submit(&p.tmOut, box, t.g * p.out_gcs + t.n_tile * 128 + oc, row0, t.b, false);
+    }
+  } else {  // NS2_EPI_WAVENET
+    static_assert(EPI != NS2_EPI_WAVENET || NACC == 2, "wavenet block needs conv + res accumulators");
+#pragma unroll 1
+    for (int oc = 0; oc < BN; oc += 64) {
+      if (tile_col0 + oc >= p.n) break;
+      const uint32_t box = st.acquire();
+#pragma unroll 1
+      for (int h = 0; h < 2; ++h) {
+        const int c = oc + h * 32;
+        const int col0 = tile_col0 + c;
+        float y[32], rr[32];
+        {
+          uint32_t rc[32], r1[32];
+          tmem_ld32(taddr + c, rc);
+          tmem_ld32(taddr + BN + c, r1);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            y[i] = __uint_as_float(rc[i]);
+            rr[i] = __uint_as_float(r1[i]);
+          }
+        }
+        const float* b0 = p.bias + t.g * p.b_grs + col0;
+        add_vec<32>(y, b0);
+        add_vec<32>(rr, b0 + p.bias1_off);
+        const float4* gm = reinterpret_cast<const float4*>(p.film + t.b * p.film_bs + t.g * p.film_gs + col0);
+        const float4* bt = reinterpret_cast<const float4*>(p.film + t.b * p.film_bs + t.g * p.film_gs + col0 + p.n);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 g4 = __ldg(gm + i), b4 = __ldg(bt + i);
+          const float ga[4] = {g4.x, g4.y, g4.z, g4.w}, be[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float z = fmaf(y[4 * i + j], ga[j], be[j]);
+            y[4 * i + j] = fmaf(tanh_fast(z), sigmoid_fast(z), rr[4 * i + j]);
+          }
+        }
+        put_bf16x32(st, box, h, y);
+      }
+      st.submit(&p.tmOut, box, t.g * p.out_gcs + tile_col0 + oc, row0, t.b, false);
     }
   }
 }
@@ -373,11 +542,14 @@ struct Gemm2Cfg {
   static constexpr int A_BYTES = BM * BK * 2;            // this CTA's 128 rows
   static constexpr int B_BYTES = (BN / 2) * BK * 2;      // this CTA's half of the B tile
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;  // multiple of 1024 for BN in {128, 176, 256}
-  static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 8 ? 8 : (200 * 1024) / STAGE_BYTES;
+  static constexpr int STG_TOTAL = 4 * 2 * STG_BYTES;    // 4 epilogue warps x 2 staging boxes
+  static constexpr int STAGES = (192 * 1024) / STAGE_BYTES > 8 ? 8 : (192 * 1024) / STAGE_BYTES;
   static constexpr int ACC_COLS = BN * NACC;
   static constexpr int ACC_STRIDE = (ACC_COLS <= 128) ? 128 : 256;  // column offset of the second stage
   static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+  static constexpr int OFF_STG = STAGES * STAGE_BYTES;
+  static constexpr int OFF_BAR = OFF_STG + STG_TOTAL;
+  static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
   static_assert(STAGE_BYTES % 1024 == 0, "stage must keep 1024-byte alignment of the swizzled tiles");
   static_assert(ACC_COLS <= 256, "accumulators of one stage must fit 256 TMEM columns");
 };
@@ -390,7 +562,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
   // identical carve-up in both CTAs of the pair (the dynamic smem base offset is the same for every CTA of a launch)
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
   uint64_t* full_bar = bars;                          // [STAGES]  used in the leader CTA only
   uint64_t* empty_bar = bars + Cfg::STAGES;           // [STAGES]  one per CTA, signalled by multicast commit
   uint64_t* tfull_bar = bars + 2 * Cfg::STAGES;       // [2]       one per CTA, multicast commit
@@ -407,6 +579,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmA);
     tma_prefetch_desc(&p.tmB);
+    tma_prefetch_desc(&p.tmOut);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < Cfg::STAGES; ++i) {
@@ -430,14 +603,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
     // =============================== TMA producer (both CTAs) ===================
     if (lane == 0) {
       uint32_t it = 0;
-      for (int tile = pair; tile < p.num_tiles; tile += num_pairs) {
+      uint32_t ti = 0;
+      for (int tile = pair; tile < p.num_tiles; tile += num_pairs, ++ti) {
         const TileCoord t = decode_tile<2 * BM>(p, tile);
         const int dil = p.dil[t.g];
+        NS2_DBG_STAMP(4);
         for (int s = 0; s < p.num_segs; ++s) {
           const ns2_gemm_seg sg = p.segs[s];
           const int row0 = t.n0 + static_cast<int>(rank) * BM - sg.shift_units * dil;
           const int a_c0 = t.g * p.a_gcs + sg.a_col_off;
-          const int b_r0 = t.g * p.b_grs + t.n_tile * BN + static_cast<int>(rank) * (BN / 2);
+          // a partial last n-tile is computed with N = bn_eff: each CTA then supplies bn_eff/2 B rows
+          const int bn_eff = (p.n - t.n_tile * BN) < BN ? (p.n - t.n_tile * BN) : BN;
+          const int b_r0 = t.g * p.b_grs + t.n_tile * BN + static_cast<int>(rank) * (bn_eff / 2);
           const int kblocks = (sg.k_len + BK - 1) / BK;
           for (int kb = 0; kb < kblocks; ++kb, ++it) {
             const uint32_t stage = it % Cfg::STAGES;
@@ -451,19 +628,24 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
             tma_load_2d_2sm(smem_u32(sa + Cfg::A_BYTES), &p.tmB, fb_leader, sg.b_col_off + kb * BK, b_r0);
           }
         }
+        NS2_DBG_STAMP(5);
       }
     }
   } else if (warp == 1) {
     // =============================== MMA issuer (leader CTA only) ================
     if (leader && lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_f16(2 * BM, BN, /*bf16*/ 1, 0, 0);
       uint32_t it = 0;
       uint32_t ti = 0;
       for (int tile = pair; tile < p.num_tiles; tile += num_pairs, ++ti) {
+        const int n_tile = tile % p.tiles_n;
+        const int bn_eff = (p.n - n_tile * BN) < BN ? (p.n - n_tile * BN) : BN;
+        const uint32_t idesc = umma_idesc_f16(2 * BM, bn_eff, /*bf16*/ 1, 0, 0);
         const uint32_t as = ti & 1;
         const uint32_t aphase = (ti >> 1) & 1;
+        NS2_DBG_STAMP(0);
         mbar_wait(smem_u32(&tempty_bar[as]), aphase ^ 1);
         tc_fence_after();
+        NS2_DBG_STAMP(1);
         uint32_t started = 0;
         for (int s = 0; s < p.num_segs; ++s) {
           const int acc = p.segs[s].acc;
@@ -474,6 +656,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
             const uint32_t phase = (it / Cfg::STAGES) & 1;
             mbar_wait(smem_u32(&full_bar[stage]), phase);
             tc_fence_after();
+            if (s == 0 && kb == 0) NS2_DBG_STAMP(2);
             const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
             const uint64_t da = umma_desc_sw128(sa, 16, 1024);
             const uint64_t db = umma_desc_sw128(sa + Cfg::A_BYTES, 16, 1024);
@@ -485,24 +668,35 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
           }
         }
         tc_commit_2cta(smem_u32(&tfull_bar[as]), 0b11);  // both CTAs' epilogues may read their 128 rows
+        NS2_DBG_STAMP(3);
       }
     }
   } else if (warp >= 4) {
     // =============================== epilogue (both CTAs) =======================
     const int ew = warp - 4;
+    Stager st;
+    st.base = smem_u32(smem + Cfg::OFF_STG + ew * 2 * STG_BYTES);
+    st.count = 0;
+    st.lane = lane;
     uint32_t ti = 0;
     for (int tile = pair; tile < p.num_tiles; tile += num_pairs, ++ti) {
       const TileCoord t = decode_tile<2 * BM>(p, tile);
       const uint32_t as = ti & 1;
       const uint32_t aphase = (ti >> 1) & 1;
+      if (ew == 0 && lane == 0) NS2_DBG_STAMP(6);
       mbar_wait(smem_u32(&tfull_bar[as]), aphase);
       tc_fence_after();
+      if (ew == 0 && lane == 0) NS2_DBG_STAMP(7);
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + as * Cfg::ACC_STRIDE;
-      epilogue_tile<BN, NACC, EPI>(p, t, taddr, t.n0 + static_cast<int>(rank) * BM + ew * 32 + lane);
+      if (!(p.debug & 4))
+        epilogue_tile_tma<BN, NACC, EPI>(p, t, taddr, t.n0 + static_cast<int>(rank) * BM + ew * 32, st);
+      // all TMEM reads of this tile are complete: hand the accumulator stage back to the leader's MMA warp
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(&tempty_bar[as]), 0));
+      if (ew == 0 && lane == 0) NS2_DBG_STAMP(8);
     }
+    if (lane == 0) tma_store_wait_all();  // staging smem must outlive the bulk stores that read it
   }
 
   // neither CTA may free TMEM / exit while its peer can still touch it (MMA writes, remote barrier arrives)
@@ -555,6 +749,13 @@ static int launch_gemm2(const GemmDev& dev, cudaStream_t stream) {
 
 }  // namespace ns2
 
+extern "C" int ns2_debug_gemm_timeline(long long* dst_host, int n) {
+  // bring-up aid (not part of the public header): copy the clock64 stamps recorded under NS2_GEMM_DEBUG=8
+  if (n > 16 * 64) n = 16 * 64;
+  cudaError_t e = cudaMemcpyFromSymbol(dst_host, ns2::g_gemm_dbg, sizeof(long long) * n);
+  return e == cudaSuccess ? 0 : -2;
+}
+
 extern "C" int ns2_gemm(const ns2_gemm_args* a, ns2_stream_t stream_) {
   using namespace ns2;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
@@ -599,11 +800,18 @@ extern "C" int ns2_gemm(const ns2_gemm_args* a, ns2_stream_t stream_) {
                 "ns2_gemm: resid must be 16-byte aligned");
 
   // ---- kernel / tile selection ----
-  const bool pair = a->a_rows > BM;  // CTA pairs need > 128 positions per batch to fill both halves
+  const int n_out = (a->epilogue == NS2_EPI_GEGLU) ? a->n / 2 : a->n;
+  const bool out_f32 = a->epilogue == NS2_EPI_F32;
+  // CTA pairs need > 128 positions per batch to fill both halves; their TMA-store epilogue needs whole 128-byte
+  // column chunks and can only fold a residual that aliases the output (reduce-add)
+  bool pair = a->a_rows > BM;
+  if (!out_f32 && n_out % 64 != 0) pair = false;
+  if (out_f32 && a->resid != nullptr && a->resid != a->out) pair = false;
+  if (out_f32 && a->resid != nullptr && a->resid_row_stride != a->out_row_stride) pair = false;
   int bn;
   if (a->epilogue == NS2_EPI_WAVENET) bn = 128;
   else if (a->epilogue == NS2_EPI_GEGLU) bn = 256;
-  else if (pair) bn = (a->n % 256 == 0) ? 256 : (a->n % 176 == 0 ? 176 : (a->n >= 1024 ? 256 : 128));
+  else if (pair) bn = a->n >= 256 ? 256 : 128;
   else bn = (a->n % 256 == 0 && a->n >= 1024) ? 256 : 128;
   const int tile_rows = pair ? 2 * BM : BM;
 
@@ -622,6 +830,18 @@ extern "C" int ns2_gemm(const ns2_gemm_args* a, ns2_stream_t stream_) {
     const uint32_t box[2] = {BK, (uint32_t)(pair ? bn / 2 : bn)};
     int rc = make_tmap_16bit(&dev.tmB, a->B, 2, dims, strides, box);
     if (rc != kOk) return rc;
+  }
+  if (pair) {
+    const uint64_t es = out_f32 ? 4 : 2;
+    const uint64_t dims[3] = {(uint64_t)(a->groups - 1) * a->out_group_col_stride + n_out, (uint64_t)a->a_rows,
+                              (uint64_t)a->a_batches};
+    const uint64_t strides[3] = {es, (uint64_t)a->out_row_stride * es,
+                                 (uint64_t)a->a_rows * a->out_row_stride * es};
+    const uint32_t box[3] = {(uint32_t)(128 / es), 32, 1};
+    int rc = out_f32 ? make_tmap_f32(&dev.tmOut, a->out, 3, dims, strides, box)
+                     : make_tmap_16bit(&dev.tmOut, a->out, 3, dims, strides, box);
+    if (rc != kOk) return rc;
+    dev.reduce_add = (out_f32 && a->resid != nullptr) ? 1 : 0;
   }
   dev.tiles_n = (a->n + bn - 1) / bn;
   dev.tiles_per_batch = (a->a_rows + tile_rows - 1) / tile_rows;
@@ -645,17 +865,19 @@ extern "C" int ns2_gemm(const ns2_gemm_args* a, ns2_stream_t stream_) {
   dev.film = a->film;
   dev.film_bs = a->film_batch_stride;
   dev.film_gs = a->film_group_stride;
+  {
+    const char* dbg = getenv("NS2_GEMM_DEBUG");
+    dev.debug = dbg ? atoi(dbg) : 0;
+  }
 
   if (pair) {
     switch (a->epilogue) {
       case NS2_EPI_BF16:
-        return bn == 256   ? launch_gemm2<256, 1, NS2_EPI_BF16>(dev, stream)
-               : bn == 176 ? launch_gemm2<176, 1, NS2_EPI_BF16>(dev, stream)
-                           : launch_gemm2<128, 1, NS2_EPI_BF16>(dev, stream);
+        return bn == 256 ? launch_gemm2<256, 1, NS2_EPI_BF16>(dev, stream)
+                         : launch_gemm2<128, 1, NS2_EPI_BF16>(dev, stream);
       case NS2_EPI_F32:
-        return bn == 256   ? launch_gemm2<256, 1, NS2_EPI_F32>(dev, stream)
-               : bn == 176 ? launch_gemm2<176, 1, NS2_EPI_F32>(dev, stream)
-                           : launch_gemm2<128, 1, NS2_EPI_F32>(dev, stream);
+        return bn == 256 ? launch_gemm2<256, 1, NS2_EPI_F32>(dev, stream)
+                         : launch_gemm2<128, 1, NS2_EPI_F32>(dev, stream);
       case NS2_EPI_GEGLU:
         return launch_gemm2<256, 1, NS2_EPI_GEGLU>(dev, stream);
       case NS2_EPI_WAVENET:

@@ -29,8 +29,8 @@ static void resolve_encode() {
     g_encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
 }
 
-int make_tmap_16bit(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
-                    const uint64_t* strides_bytes, const uint32_t* box) {
+static int make_tmap(CUtensorMap* out, CUtensorMapDataType dtype, const void* base, int rank,
+                     const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box) {
   std::call_once(g_encode_once, resolve_encode);
   if (!g_encode) return set_error(kErrCuda, "cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
   if ((reinterpret_cast<uintptr_t>(base) & 15) != 0)
@@ -50,7 +50,7 @@ int make_tmap_16bit(CUtensorMap* out, const void* base, int rank, const uint64_t
                          (unsigned long long)strides_bytes[i], i);
     }
   }
-  CUresult r = g_encode(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), gdim,
+  CUresult r = g_encode(out, dtype, rank, const_cast<void*>(base), gdim,
                         gstr, bx, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -62,6 +62,15 @@ int make_tmap_16bit(CUtensorMap* out, const void* base, int rank, const uint64_t
                      rank > 2 ? box[2] : 0);
   }
   return kOk;
+}
+
+int make_tmap_16bit(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                    const uint64_t* strides_bytes, const uint32_t* box) {
+  return make_tmap(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, base, rank, dims, strides_bytes, box);
+}
+int make_tmap_f32(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                  const uint64_t* strides_bytes, const uint32_t* box) {
+  return make_tmap(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, base, rank, dims, strides_bytes, box);
 }
 
 int num_sms() {

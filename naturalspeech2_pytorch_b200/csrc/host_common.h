@@ -26,6 +26,9 @@ const char* last_error_cstr();
 // Swizzle is always 128 B (inner box = 64 elements = 128 bytes), OOB elements read as zero.
 int make_tmap_16bit(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
                     const uint64_t* strides_bytes, const uint32_t* box);
+// Same for fp32 tensors (TMA stores / reduce-adds of the fp32 residual stream): inner box = 32 elements.
+int make_tmap_f32(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                  const uint64_t* strides_bytes, const uint32_t* box);
 
 #define NS2_CUDA_CHECK(expr)                                                                  \
   do {                                                                                        \

@@ -92,3 +92,10 @@ if "rvq" in which:
     codes = torch.empty(F, 8, device=dev, dtype=torch.int64)
     timeit("rvq_encode 1M x 8 x 1024", lambda: ops.rvq_encode(x, cb, prep, codes=codes), flops=2.0 * F * 8 * 1024 * 128)
     print(f"  -> {F * 8 / 1e6:.1f} Mcodes per launch")
+if "sweep" in which:
+    # plain bf16 GEMMs, M = 32768: isolates tile shape / K depth effects of the CTA-pair kernel
+    for (n, k) in [(1536, 512), (1536, 4096), (2048, 4096), (1408, 4224), (512, 4096), (512, 512), (1024, 1024)]:
+        a = (torch.randn(B, N, k, device=dev) * 0.5).to(bf)
+        w = (torch.randn(n, k, device=dev) * 0.02).to(bf)
+        out = torch.empty(B, N, n, device=dev, dtype=bf)
+        timeit(f"plain gemm N={n} K={k}", lambda: ops.gemm(a, w, out, n=n, epilogue=ops.EPI_BF16), flops=2.0 * B * N * n * k)
