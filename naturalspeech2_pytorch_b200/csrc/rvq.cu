@@ -10,13 +10,13 @@
 // are re-scored exactly in fp64 from the fp32 operands, so the emitted index is the exact argmin
 // (ties -> lowest index) — bit-exact against the fp64 oracle — while >99% of the flops stay on tensor cores.
 //
-// One CTA per 128 frames, 192 threads:
-//   warps 0-3  "row" threads: thread t owns frame t; its fp32 residual (128 values) lives in shared memory
-//              (transposed, so every access is bank-conflict free) for all Q stages; builds the fp16 A tile
-//              in swizzled smem, scans the TMEM score tiles keeping the 4 best codes, re-scores near-ties
-//              in fp64, subtracts the chosen fp32 codeword
-//   warp 4     TMA producer: streams the fp16 codebooks (128 codes x 128 dims per chunk) through a 3-deep ring
-//   warp 5     tcgen05.mma issuer: D[128 frames x 128 codes] per chunk, double-buffered in TMEM
+// One CTA per 128 frames, 320 threads:
+//   warps 0-7  scan threads: two threads per frame (TMEM lane), each scanning 64 of every 128 score columns with a
+//              branch-free top-4 on packed (score|index) keys; fp32 residuals live in padded shared memory for all
+//              Q stages; the same threads build the fp16 A tile, re-score near-ties in fp64 (per lane, or
+//              warp-cooperatively for crowded 32-code blocks / bands) and subtract the chosen fp32 codeword
+//   warp 8     TMA producer: streams the fp16 codebooks (128 codes x 128 dims per chunk) through a 3-deep ring
+//   warp 9     tcgen05.mma issuer: D[128 frames x 128 codes] per chunk, double-buffered in TMEM
 #include "ptx.cuh"
 #include "host_common.h"
 #include "../../include/ns2_b200.h"
@@ -34,14 +34,19 @@ constexpr int BC = 128;       // codes per chunk
 constexpr int A_BYTES = BF * D * 2;   // 32 KB: two 64-dim swizzle atoms
 constexpr int B_BYTES = BC * D * 2;   // 32 KB per chunk
 constexpr int RING = 3;
+constexpr int RSTRIDE = D + 4;        // floats per residual row: +4 keeps per-thread float4 row reads conflict-free
+constexpr int MAX_K = 2048;
 constexpr int OFF_A = 0;
 constexpr int OFF_B = OFF_A + A_BYTES;
-constexpr int OFF_R = OFF_B + RING * B_BYTES;        // fp32 residuals, transposed [dim][frame]: 64 KB
-constexpr int OFF_CN2 = OFF_R + BF * D * 4;          // ||c||^2 of the current stage
-constexpr int MAX_K = 2048;
-constexpr int OFF_BAR = OFF_CN2 + MAX_K * 4;
+constexpr int OFF_R = OFF_B + RING * B_BYTES;        // fp32 residuals, row-major padded: 67.6 KB
+constexpr int OFF_CN2 = OFF_R + BF * RSTRIDE * 4;    // ||c||^2 of the current stage
+constexpr int OFF_MERGE = OFF_CN2 + MAX_K * 4;       // top-4 keys of the second column half, per row
+constexpr int OFF_ROWP = OFF_MERGE + BF * 4 * 4;     // per-row {scale, dscale, margin, |r|^2}
+constexpr int OFF_SEL = OFF_ROWP + BF * 4 * 4;       // chosen code per row (this stage)
+constexpr int OFF_BAR = OFF_SEL + BF * 4;
 constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
 constexpr int TMEM_COLS = 256;
+constexpr int SCAN_THREADS = 256;     // warps 0-7: quarter = warp & 3 (TMEM lanes), column half = warp >> 2
 }  // namespace rvq
 
 struct RvqDev {
@@ -51,24 +56,26 @@ struct RvqDev {
   const float* cn2;           // (Q, K)
   const float* meta;          // (Q, 2): max ||c||, 2^e_q
   long long* codes;           // (F, Q)
-  unsigned long long* stats;  // optional: [0] rows*stages, [1] ambiguous, [2] overflow full scans
+  unsigned long long* stats;  // optional: [0] lookups, [1] near-ties re-scored, [2] full scans, [3] sub-chunk scans
   long long num_frames;
   int Q, K;
 };
 
-// exact squared distance in fp64 between one frame's residual (column `rcol` of the transposed smem tile,
-// stride BF floats) and one fp32 codeword.  Four independent accumulators (dims i mod 4) break the DFMA
-// dependency chain; the summation order is fixed, so equal inputs always give bit-equal results.
-__device__ __forceinline__ double exact_dist(const float* rcol, const float* __restrict__ c) {
+// Exact squared distance in fp64 between one residual row (shared memory, contiguous) and one fp32 codeword.
+// Four independent accumulators (dims i mod 4) break the DFMA dependency chain; the summation order is fixed, so
+// equal inputs always give bit-equal results (ties between duplicate codewords resolve by index).
+__device__ __forceinline__ double exact_dist(const float* rrow, const float* __restrict__ c) {
   double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
   const float4* c4 = reinterpret_cast<const float4*>(c);
+  const float4* r4 = reinterpret_cast<const float4*>(rrow);
 #pragma unroll 8
   for (int i = 0; i < rvq::D / 4; ++i) {
     const float4 v = __ldg(c4 + i);
-    const double d0 = static_cast<double>(rcol[(4 * i + 0) * rvq::BF]) - static_cast<double>(v.x);
-    const double d1 = static_cast<double>(rcol[(4 * i + 1) * rvq::BF]) - static_cast<double>(v.y);
-    const double d2 = static_cast<double>(rcol[(4 * i + 2) * rvq::BF]) - static_cast<double>(v.z);
-    const double d3 = static_cast<double>(rcol[(4 * i + 3) * rvq::BF]) - static_cast<double>(v.w);
+    const float4 r = r4[i];
+    const double d0 = static_cast<double>(r.x) - static_cast<double>(v.x);
+    const double d1 = static_cast<double>(r.y) - static_cast<double>(v.y);
+    const double d2 = static_cast<double>(r.z) - static_cast<double>(v.z);
+    const double d3 = static_cast<double>(r.w) - static_cast<double>(v.w);
     a0 = fma(d0, d0, a0);
     a1 = fma(d1, d1, a1);
     a2 = fma(d2, d2, a2);
@@ -77,16 +84,44 @@ __device__ __forceinline__ double exact_dist(const float* rcol, const float* __r
   return (a0 + a1) + (a2 + a3);
 }
 
-__global__ void __launch_bounds__(192, 1) rvq_encode_kernel(const __grid_constant__ RvqDev p) {
+__device__ __forceinline__ void scan_barrier() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+// sorted insert of a key into the ascending 4-tuple (g0..g3): 7 min/max, no branches
+__device__ __forceinline__ void insert4(float key, float& g0, float& g1, float& g2, float& g3) {
+  float t = key, lo;
+  lo = fminf(g0, t); t = fmaxf(g0, t); g0 = lo;
+  lo = fminf(g1, t); t = fmaxf(g1, t); g1 = lo;
+  lo = fminf(g2, t); t = fmaxf(g2, t); g2 = lo;
+  g3 = fminf(g3, t);
+}
+
+// (distance, index) lexicographic minimum across the warp
+__device__ __forceinline__ void warp_argmin(double& d, int& k) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double od = __shfl_xor_sync(0xffffffffu, d, o);
+    const int ok = __shfl_xor_sync(0xffffffffu, k, o);
+    if (od < d || (od == d && ok < k)) { d = od; k = ok; }
+  }
+}
+
+// Approximate scores are carried as "keys": the fp32 score with its low mantissa bits replaced by the code index,
+// so that min/max on the keys sorts (score, index) pairs without branches or separate index registers.
+// Low 11 bits = index (K <= 2048); the 2^-12 relative truncation is folded into the re-score margin.
+__global__ void __launch_bounds__(320, 1) rvq_encode_kernel(const __grid_constant__ RvqDev p) {
   using namespace rvq;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
+  float* R = reinterpret_cast<float*>(smem + OFF_R);
   float* cn2_s = reinterpret_cast<float*>(smem + OFF_CN2);
+  float* merge_s = reinterpret_cast<float*>(smem + OFF_MERGE);
+  float4* rowp_s = reinterpret_cast<float4*>(smem + OFF_ROWP);
+  int* sel_s = reinterpret_cast<int*>(smem + OFF_SEL);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
   uint64_t* b_full = bars + 0;    // [RING]
   uint64_t* b_empty = bars + 3;   // [RING]
-  uint64_t* a_full = bars + 6;    // row threads -> MMA: A tile of this stage written
+  uint64_t* a_full = bars + 6;    // scan threads -> MMA: A tile of this stage written
   uint64_t* d_full = bars + 7;    // [2]
   uint64_t* d_empty = bars + 9;   // [2]
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 11);
@@ -95,16 +130,16 @@ __global__ void __launch_bounds__(192, 1) rvq_encode_kernel(const __grid_constan
   const long long f0 = static_cast<long long>(blockIdx.x) * BF;
   const int chunks = p.K / BC;
 
-  if (warp == 4 && lane == 0) tma_prefetch_desc(&p.tmB);
-  if (warp == 5 && lane == 0) {
+  if (warp == 8 && lane == 0) tma_prefetch_desc(&p.tmB);
+  if (warp == 9 && lane == 0) {
     for (int i = 0; i < RING; ++i) {
       mbar_init(smem_u32(&b_full[i]), 1);
       mbar_init(smem_u32(&b_empty[i]), 1);
     }
-    mbar_init(smem_u32(a_full), 128);
+    mbar_init(smem_u32(a_full), SCAN_THREADS);
     for (int i = 0; i < 2; ++i) {
       mbar_init(smem_u32(&d_full[i]), 1);
-      mbar_init(smem_u32(&d_empty[i]), 128);
+      mbar_init(smem_u32(&d_empty[i]), SCAN_THREADS);
     }
     fence_barrier_init();
   }
@@ -114,7 +149,7 @@ __global__ void __launch_bounds__(192, 1) rvq_encode_kernel(const __grid_constan
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
 
-  if (warp == 4) {
+  if (warp == 8) {
     // ================================ TMA producer ================================
     if (lane == 0) {
       uint32_t it = 0;
@@ -131,7 +166,7 @@ __global__ void __launch_bounds__(192, 1) rvq_encode_kernel(const __grid_constan
         }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == 9) {
     // ================================ MMA issuer ==================================
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_f16(BF, BC, /*fp16*/ 0, 0, 0);
@@ -159,147 +194,187 @@ __global__ void __launch_bounds__(192, 1) rvq_encode_kernel(const __grid_constan
       }
     }
   } else {
-    // ================================ row threads =================================
-    const int row = warp * 32 + lane;
+    // ================================ scan threads ================================
+    const int quarter = warp & 3, half = warp >> 2;
+    const int row = quarter * 32 + lane;       // frame owned (together with the thread of the other half)
     const long long f = f0 + row;
     const bool live = f < p.num_frames;
-    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
-    float* rcol = reinterpret_cast<float*>(smem + OFF_R) + row;  // element i of this frame: rcol[i * BF]
-    {
-      const float4* src = reinterpret_cast<const float4*>(p.frames + (live ? f : 0) * D);
-#pragma unroll 4
-      for (int i = 0; i < D / 4; ++i) {
-        const float4 v = live ? __ldg(src + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-        rcol[(4 * i + 0) * BF] = v.x;
-        rcol[(4 * i + 1) * BF] = v.y;
-        rcol[(4 * i + 2) * BF] = v.z;
-        rcol[(4 * i + 3) * BF] = v.w;
-      }
+    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+    float* rrow = R + row * RSTRIDE;
+
+    // cooperative, coalesced load of the 128 frames: warp w fills rows [16w, 16w+16)
+    for (int r = warp * 16; r < warp * 16 + 16; ++r) {
+      const long long fr = f0 + r;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (fr < p.num_frames) v = __ldg(reinterpret_cast<const float4*>(p.frames + fr * D) + lane);
+      reinterpret_cast<float4*>(R + r * RSTRIDE)[lane] = v;
     }
-    unsigned long long n_ambig = 0, n_full = 0;
+    unsigned long long n_ambig = 0, n_full = 0, n_sub = 0;
     uint32_t it = 0;
     for (int q = 0; q < p.Q; ++q) {
-      // ---- stage prologue: ||c||^2 table, row scale and norm, fp16 A tile ----
-      asm volatile("bar.sync 1, 128;" ::: "memory");  // everyone is done with the previous cn2 table
-      for (int i = row; i < p.K; i += 128) cn2_s[i] = __ldg(p.cn2 + q * p.K + i);
-      float amax = 0.f, ss = 0.f;
+      scan_barrier();  // residuals of this stage are in place (frame load / previous stage's update)
+      const float cmax = __ldg(p.meta + 2 * q), cscale = __ldg(p.meta + 2 * q + 1);
+      if (half == 0) {
+        // row scale (exact power of two into fp16 range), |r|^2, filter margin
+        float amax = 0.f, ss = 0.f;
 #pragma unroll 8
-      for (int i = 0; i < D; ++i) {
-        const float v = rcol[i * BF];
-        amax = fmaxf(amax, fabsf(v));
-        ss = fmaf(v, v, ss);
+        for (int i = 0; i < D / 4; ++i) {
+          const float4 v = reinterpret_cast<const float4*>(rrow)[i];
+          amax = fmaxf(fmaxf(amax, fabsf(v.x)), fmaxf(fabsf(v.y), fmaxf(fabsf(v.z), fabsf(v.w))));
+          ss = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, ss))));
+        }
+        int ex = 0;
+        if (amax > 0.f) (void)frexpf(amax, &ex);  // amax = m * 2^ex, m in [0.5, 1)
+        const float xs = ldexpf(1.0f, -ex);
+        const float dscale = -2.0f * ldexpf(cscale, ex);  // s~ = cn2 + dscale * dot'
+        // |s~_k - s_k| <= E16 = 2 * 1.05 * 2^-10 * ||r|| * max||c||  (fp16 operand rounding, fp32 accumulate)
+        const float e16 = 2.0f * 0.001026f * sqrtf(ss) * 1.001f * cmax;
+        rowp_s[row] = make_float4(xs, dscale, e16, ss);
       }
-      int ex = 0;
-      if (amax > 0.f) (void)frexpf(amax, &ex);  // amax = m * 2^ex, m in [0.5, 1)
-      const float xs = ldexpf(1.0f, -ex);      // exact power-of-two scale into fp16 range
+      for (int i = threadIdx.x; i < p.K; i += SCAN_THREADS) cn2_s[i] = __ldg(p.cn2 + q * p.K + i);
+      scan_barrier();
+      const float4 rp = rowp_s[row];
+      // ---- fp16 A tile: this thread converts dims [64*half, 64*half + 64) of its row into atom `half` ----
       {
-        uint8_t* arow = smem + OFF_A + row * 128;
-#pragma unroll 2
-        for (int ch = 0; ch < 16; ++ch) {  // 16 chunks of 8 halves
-          uint32_t w[4];
+        const float xs = rp.x;
+        uint8_t* arow = smem + OFF_A + half * (BF * 128) + row * 128;
+        const float4* src = reinterpret_cast<const float4*>(rrow + half * 64);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const __half2 h = __floats2half2_rn(rcol[(ch * 8 + 2 * j) * BF] * xs,
-                                                rcol[(ch * 8 + 2 * j + 1) * BF] * xs);
-            w[j] = *reinterpret_cast<const uint32_t*>(&h);
-          }
-          uint8_t* atom = arow + (ch >> 3) * (BF * 128);
-          *reinterpret_cast<uint4*>(atom + (((ch & 7) ^ (row & 7)) << 4)) =
-              make_uint4(w[0], w[1], w[2], w[3]);
+        for (int ch = 0; ch < 8; ++ch) {  // 8 chunks of 8 halves
+          const float4 v0 = src[2 * ch], v1 = src[2 * ch + 1];
+          const __half2 h0 = __floats2half2_rn(v0.x * xs, v0.y * xs), h1 = __floats2half2_rn(v0.z * xs, v0.w * xs);
+          const __half2 h2 = __floats2half2_rn(v1.x * xs, v1.y * xs), h3 = __floats2half2_rn(v1.z * xs, v1.w * xs);
+          *reinterpret_cast<uint4*>(arow + ((ch ^ (row & 7)) << 4)) =
+              make_uint4(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1),
+                         *reinterpret_cast<const uint32_t*>(&h2), *reinterpret_cast<const uint32_t*>(&h3));
         }
       }
       fence_proxy_async_smem();
       mbar_arrive(smem_u32(a_full));
-      asm volatile("bar.sync 1, 128;" ::: "memory");  // cn2 table visible to all row threads
 
-      const float cmax = __ldg(p.meta + 2 * q), cscale = __ldg(p.meta + 2 * q + 1);
-      const float dscale = -2.0f * ldexpf(cscale, ex);  // s~ = cn2 + dscale * dot'
-      // rigorous filter margin (see header comment); 1.001 covers the fp32 rounding of ||r|| itself
-      const float margin2 = 2.0f * (2.0f * 0.001026f /*1.05 * 2^-10*/ * sqrtf(ss) * 1.001f * cmax);
-
-      // ---- scan all codes, keep the four best approximate scores ----
-      float b0 = INFINITY, b1 = INFINITY, b2 = INFINITY, b3 = INFINITY;
-      int i0 = 0, i1 = 0, i2 = 0;
+      // ---- scan this thread's 64 columns of every 128-code chunk: branch-free top-4 on packed keys ----
+      const float dscale = rp.y;
+      float g0 = INFINITY, g1 = INFINITY, g2 = INFINITY, g3 = INFINITY;
       for (int c = 0; c < chunks; ++c, ++it) {
         const uint32_t buf = it & 1, dph = (it >> 1) & 1;
         mbar_wait(smem_u32(&d_full[buf]), dph);
         tc_fence_after();
 #pragma unroll 1
-        for (int sub = 0; sub < BC / 32; ++sub) {
+        for (int sub = 0; sub < 2; ++sub) {
           uint32_t v[32];
-          tmem_ld32(lane_addr + buf * BC + sub * 32, v);
+          tmem_ld32(lane_addr + buf * BC + half * 64 + sub * 32, v);
           tmem_ld_wait();
-          const int kbase = c * BC + sub * 32;
+          const int sub_id = c * 4 + half * 2 + sub;   // 32-code block index: code = sub_id * 32 + i
+          const float* cn = cn2_s + sub_id * 32;
+          // local top-2 of the 32 scores, index i in the low 5 bits; two interleaved trackers for ILP
+          float a0 = INFINITY, a1 = INFINITY, b0 = INFINITY, b1 = INFINITY;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float s = fmaf(dscale, __uint_as_float(v[i]), cn2_s[kbase + i]);
-            if (s < b3) {  // rare after the first few codes: insertion into the sorted top-4
-              const int k = kbase + i;
-              if (s < b0) { b3 = b2; b2 = b1; i2 = i1; b1 = b0; i1 = i0; b0 = s; i0 = k; }
-              else if (s < b1) { b3 = b2; b2 = b1; i2 = i1; b1 = s; i1 = k; }
-              else if (s < b2) { b3 = b2; b2 = s; i2 = k; }
-              else { b3 = s; }
-            }
+          for (int i = 0; i < 32; i += 2) {
+            const float s0 = fmaf(dscale, __uint_as_float(v[i]), cn[i]);
+            const float s1 = fmaf(dscale, __uint_as_float(v[i + 1]), cn[i + 1]);
+            const float k0 = __uint_as_float((__float_as_uint(s0) & 0xFFFFFFE0u) | static_cast<uint32_t>(i));
+            const float k1 = __uint_as_float((__float_as_uint(s1) & 0xFFFFFFE0u) | static_cast<uint32_t>(i + 1));
+            float t = fmaxf(a0, k0); a0 = fminf(a0, k0); a1 = fminf(a1, t);
+            t = fmaxf(b0, k1); b0 = fminf(b0, k1); b1 = fminf(b1, t);
           }
+          const float l0 = fminf(a0, b0);
+          const float l1 = fminf(fmaxf(a0, b0), fminf(a1, b1));
+          // widen the index field to 11 bits (block id above the 5 local bits) and merge into the global top-4
+          const uint32_t blk = static_cast<uint32_t>(sub_id) << 5;
+          insert4(__uint_as_float((__float_as_uint(l0) & 0xFFFFF81Fu) | blk), g0, g1, g2, g3);
+          insert4(__uint_as_float((__float_as_uint(l1) & 0xFFFFF81Fu) | blk), g0, g1, g2, g3);
         }
         tc_fence_before();
         mbar_arrive(smem_u32(&d_empty[buf]));
       }
 
-      // ---- exact decision ----
-      const float* cbq = p.codebooks + static_cast<long long>(q) * p.K * D;
-      int best = i0;
-      const float lim = b0 + margin2;
-      const bool overflow = b3 <= lim;  // more than three codes inside the uncertainty band
-      if (b1 <= lim && !overflow) {
-        ++n_ambig;
-        double dbest = exact_dist(rcol, cbq + static_cast<long long>(i0) * D);
-        const double d1 = exact_dist(rcol, cbq + static_cast<long long>(i1) * D);
-        if (d1 < dbest || (d1 == dbest && i1 < best)) { dbest = d1; best = i1; }
-        if (b2 <= lim) {
-          const double d2 = exact_dist(rcol, cbq + static_cast<long long>(i2) * D);
-          if (d2 < dbest || (d2 == dbest && i2 < best)) { dbest = d2; best = i2; }
+      // ---- merge the two column halves of each row ----
+      if (half == 1) *reinterpret_cast<float4*>(merge_s + row * 4) = make_float4(g0, g1, g2, g3);
+      scan_barrier();
+      if (half == 0) {
+        const float4 o = *reinterpret_cast<const float4*>(merge_s + row * 4);
+        insert4(o.x, g0, g1, g2, g3);
+        insert4(o.y, g0, g1, g2, g3);
+        insert4(o.z, g0, g1, g2, g3);
+        insert4(o.w, g0, g1, g2, g3);
+        // ---- exact decision ----
+        // Candidates = every code whose key is within the error band of the best key.  A band member can only be
+        // missing from (g0,g1,g2) if g3 is in the band too (-> full scan) or if it was 3rd+ inside its 32-code block,
+        // in which case two better band members share that block (-> that block is scanned exactly).
+        const float* cbq = p.codebooks + static_cast<long long>(q) * p.K * D;
+        const float etrunc = 0.000244140625f * 1.01f * (fabsf(g0) + 2.0f * rp.z);  // 2^-12 relative key truncation
+        const float lim = g0 + 2.0f * (rp.z + etrunc);
+        const int i0 = __float_as_uint(g0) & 0x7FF, i1 = __float_as_uint(g1) & 0x7FF, i2 = __float_as_uint(g2) & 0x7FF;
+        const bool in1 = g1 <= lim, in2 = g2 <= lim;
+        const bool overflow = g3 <= lim;
+        int best = i0;
+        double dbest = INFINITY;
+        int conflict_blk = -1;
+        if (in1 && !overflow) {
+          ++n_ambig;
+          dbest = exact_dist(rrow, cbq + static_cast<long long>(i0) * D);
+          const double d1 = exact_dist(rrow, cbq + static_cast<long long>(i1) * D);
+          if (d1 < dbest || (d1 == dbest && i1 < best)) { dbest = d1; best = i1; }
+          if ((i0 >> 5) == (i1 >> 5)) conflict_blk = i0 >> 5;
+          if (in2) {
+            const double d2 = exact_dist(rrow, cbq + static_cast<long long>(i2) * D);
+            if (d2 < dbest || (d2 == dbest && i2 < best)) { dbest = d2; best = i2; }
+            if ((i2 >> 5) == (i0 >> 5)) conflict_blk = i0 >> 5;
+            else if ((i2 >> 5) == (i1 >> 5)) conflict_blk = i1 >> 5;
+          }
         }
+        // rows with two band members in one 32-code block: the warp scores that block exactly, one code per lane
+        unsigned cmask = __ballot_sync(0xffffffffu, conflict_blk >= 0);
+        while (cmask) {
+          const int src = __ffs(cmask) - 1;
+          cmask &= cmask - 1;
+          const int blk = __shfl_sync(0xffffffffu, conflict_blk, src);
+          int k = blk * 32 + lane;
+          double dk = exact_dist(R + (quarter * 32 + src) * RSTRIDE, cbq + static_cast<long long>(k) * D);
+          warp_argmin(dk, k);
+          if (lane == src) {
+            ++n_sub;
+            if (dk < dbest || (dk == dbest && k < best)) { dbest = dk; best = k; }
+          }
+        }
+        // rows with four or more band members (rare): the warp scans the whole codebook exactly for that row
+        unsigned omask = __ballot_sync(0xffffffffu, overflow);
+        if (overflow) { ++n_ambig; ++n_full; }
+        while (omask) {
+          const int src = __ffs(omask) - 1;
+          omask &= omask - 1;
+          const float* rsrc = R + (quarter * 32 + src) * RSTRIDE;
+          double dmin = INFINITY;
+          int kmin = 0x7fffffff;
+          for (int k = lane; k < p.K; k += 32) {
+            const double dk = exact_dist(rsrc, cbq + static_cast<long long>(k) * D);
+            if (dk < dmin) { dmin = dk; kmin = k; }  // k ascending per lane: first minimum kept
+          }
+          warp_argmin(dmin, kmin);
+          if (lane == src) best = kmin;
+        }
+        sel_s[row] = best;
+        if (live) p.codes[f * p.Q + q] = best;
       }
-      // overflow rows (rare): the whole warp scans the codebook exactly for that one row, 32 codes per lane
-      unsigned omask = __ballot_sync(0xffffffffu, overflow);
-      if (overflow) { ++n_ambig; ++n_full; }
-      while (omask) {
-        const int src = __ffs(omask) - 1;
-        omask &= omask - 1;
-        const float* rsrc = reinterpret_cast<const float*>(smem + OFF_R) + (warp * 32 + src);
-        double dmin = INFINITY;
-        int kmin = 0x7fffffff;
-        for (int k = lane; k < p.K; k += 32) {
-          const double dk = exact_dist(rsrc, cbq + static_cast<long long>(k) * D);
-          if (dk < dmin) { dmin = dk; kmin = k; }  // k ascending per lane: first minimum kept
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          const double od = __shfl_xor_sync(0xffffffffu, dmin, o);
-          const int ok = __shfl_xor_sync(0xffffffffu, kmin, o);
-          if (od < dmin || (od == dmin && ok < kmin)) { dmin = od; kmin = ok; }
-        }
-        if (lane == src) best = kmin;
-      }
-      if (live) p.codes[f * p.Q + q] = best;
-      // ---- residual update with the exact fp32 codeword (same op as the reference) ----
+      scan_barrier();
+      // ---- residual update with the exact fp32 codeword (same op as the reference): warp w owns rows [16w, 16w+16),
+      //      each codeword is fetched with one coalesced 512-byte load ----
       {
-        const float4* cw = reinterpret_cast<const float4*>(cbq + static_cast<long long>(best) * D);
-#pragma unroll 4
-        for (int i = 0; i < D / 4; ++i) {
-          const float4 v = __ldg(cw + i);
-          rcol[(4 * i + 0) * BF] -= v.x;
-          rcol[(4 * i + 1) * BF] -= v.y;
-          rcol[(4 * i + 2) * BF] -= v.z;
-          rcol[(4 * i + 3) * BF] -= v.w;
+        const float* cbq = p.codebooks + static_cast<long long>(q) * p.K * D;
+        for (int r = warp * 16; r < warp * 16 + 16; ++r) {
+          const float4 cw = __ldg(reinterpret_cast<const float4*>(cbq + static_cast<long long>(sel_s[r]) * D) + lane);
+          float4* dst = reinterpret_cast<float4*>(R + r * RSTRIDE) + lane;
+          float4 v = *dst;
+          v.x -= cw.x; v.y -= cw.y; v.z -= cw.z; v.w -= cw.w;
+          *dst = v;
         }
       }
     }
-    if (p.stats != nullptr && live) {
+    if (p.stats != nullptr && half == 0 && live) {
       atomicAdd(p.stats + 0, static_cast<unsigned long long>(p.Q));
       if (n_ambig) atomicAdd(p.stats + 1, n_ambig);
       if (n_full) atomicAdd(p.stats + 2, n_full);
+      if (n_sub) atomicAdd(p.stats + 3, n_sub);
     }
   }
 
@@ -436,7 +511,7 @@ int ns2_rvq_encode(const float* frames, int64_t num_frames, int32_t d, const flo
   }
   const long long grid = (num_frames + rvq::BF - 1) / rvq::BF;
   NS2_REQUIRE(grid <= 0x7fffffffLL, "rvq_encode: too many frames");
-  rvq_encode_kernel<<<static_cast<unsigned>(grid), 192, rvq::SMEM_BYTES,
+  rvq_encode_kernel<<<static_cast<unsigned>(grid), 320, rvq::SMEM_BYTES,
                       static_cast<cudaStream_t>(stream)>>>(dev);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   NS2_CUDA_CHECK(cudaGetLastError());

@@ -296,7 +296,7 @@ def run_rvq():
         mism = (codes != ref)
         nm = int(mism.sum())
         print(f"[{'OK ' if nm == 0 else 'BAD'}] rvq_encode F{F} Q{Q} K{K} scale{scale}: mismatches={nm}/{F * Q} "
-              f"stats(lookups, near-ties, full scans)={stats[:3].tolist()}", flush=True)
+              f"stats(lookups, near-ties, full scans, block scans)={stats[:4].tolist()}", flush=True)
         if nm:
             bad = mism.nonzero()[:8]
             for i in bad:
