@@ -43,7 +43,8 @@ constexpr int OFF_CN2 = OFF_R + BF * RSTRIDE * 4;    // ||c||^2 of the current s
 constexpr int OFF_MERGE = OFF_CN2 + MAX_K * 4;       // top-4 keys of the second column half, per row
 constexpr int OFF_ROWP = OFF_MERGE + BF * 4 * 4;     // per-row {scale, dscale, margin, |r|^2}
 constexpr int OFF_SEL = OFF_ROWP + BF * 4 * 4;       // chosen code per row (this stage)
-constexpr int OFF_BAR = OFF_SEL + BF * 4;
+constexpr int OFF_DEC = OFF_SEL + BF * 4;            // per row {i0, i1, i2, band size | overflow << 3}
+constexpr int OFF_BAR = OFF_DEC + BF * 16;
 constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
 constexpr int TMEM_COLS = 256;
 constexpr int SCAN_THREADS = 256;     // warps 0-7: quarter = warp & 3 (TMEM lanes), column half = warp >> 2
@@ -84,6 +85,20 @@ __device__ __forceinline__ double exact_dist(const float* rrow, const float* __r
   return (a0 + a1) + (a2 + a3);
 }
 
+// Warp-cooperative variant: lane l owns dims [4l, 4l+4); one coalesced 512-byte load of the codeword, a fixed
+// butterfly reduction (so equal inputs give bit-equal results).  Every lane returns the full distance.
+__device__ __forceinline__ double coop_dist(const float4 r, const float* __restrict__ c, int lane) {
+  const float4 v = __ldg(reinterpret_cast<const float4*>(c) + lane);
+  const double d0 = static_cast<double>(r.x) - static_cast<double>(v.x);
+  const double d1 = static_cast<double>(r.y) - static_cast<double>(v.y);
+  const double d2 = static_cast<double>(r.z) - static_cast<double>(v.z);
+  const double d3 = static_cast<double>(r.w) - static_cast<double>(v.w);
+  double a = fma(d0, d0, fma(d1, d1, fma(d2, d2, d3 * d3)));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+  return a;
+}
+
 __device__ __forceinline__ void scan_barrier() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 // sorted insert of a key into the ascending 4-tuple (g0..g3): 7 min/max, no branches
@@ -118,6 +133,7 @@ __global__ void __launch_bounds__(320, 1) rvq_encode_kernel(const __grid_constan
   float* merge_s = reinterpret_cast<float*>(smem + OFF_MERGE);
   float4* rowp_s = reinterpret_cast<float4*>(smem + OFF_ROWP);
   int* sel_s = reinterpret_cast<int*>(smem + OFF_SEL);
+  int4* dec_s = reinterpret_cast<int4*>(smem + OFF_DEC);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
   uint64_t* b_full = bars + 0;    // [RING]
   uint64_t* b_empty = bars + 3;   // [RING]
@@ -297,64 +313,70 @@ __global__ void __launch_bounds__(320, 1) rvq_encode_kernel(const __grid_constan
         insert4(o.y, g0, g1, g2, g3);
         insert4(o.z, g0, g1, g2, g3);
         insert4(o.w, g0, g1, g2, g3);
-        // ---- exact decision ----
+        // ---- classify: how many keys sit inside the error band of the best key ----
         // Candidates = every code whose key is within the error band of the best key.  A band member can only be
         // missing from (g0,g1,g2) if g3 is in the band too (-> full scan) or if it was 3rd+ inside its 32-code block,
         // in which case two better band members share that block (-> that block is scanned exactly).
-        const float* cbq = p.codebooks + static_cast<long long>(q) * p.K * D;
         const float etrunc = 0.000244140625f * 1.01f * (fabsf(g0) + 2.0f * rp.z);  // 2^-12 relative key truncation
         const float lim = g0 + 2.0f * (rp.z + etrunc);
         const int i0 = __float_as_uint(g0) & 0x7FF, i1 = __float_as_uint(g1) & 0x7FF, i2 = __float_as_uint(g2) & 0x7FF;
-        const bool in1 = g1 <= lim, in2 = g2 <= lim;
-        const bool overflow = g3 <= lim;
-        int best = i0;
-        double dbest = INFINITY;
-        int conflict_blk = -1;
-        if (in1 && !overflow) {
+        const int nband = 1 + (g1 <= lim ? 1 : 0) + ((g1 <= lim && g2 <= lim) ? 1 : 0);
+        const int overflow = (g3 <= lim) ? 8 : 0;
+        dec_s[row] = make_int4(i0, i1, i2, nband | overflow);
+        sel_s[row] = i0;
+      }
+      scan_barrier();
+      // ---- exact decision, warp-cooperative: warp w owns rows [16w, 16w+16) ----
+      {
+        const float* cbq = p.codebooks + static_cast<long long>(q) * p.K * D;
+        for (int r = warp * 16; r < warp * 16 + 16; ++r) {
+          const int4 dc = dec_s[r];
+          if ((dc.w & 15) == 1) continue;  // unique candidate: the filter's winner is exact
+          const float4 rv = reinterpret_cast<const float4*>(R + r * RSTRIDE)[lane];
+          int best;
+          double dbest;
+          if (dc.w & 8) {
+            // four or more keys in the band (rare): exact scan of the whole codebook, 8 codes in flight
+            ++n_full;
+            dbest = INFINITY;
+            best = 0;
+            for (int k0 = 0; k0 < p.K; k0 += 8) {
+              double dk[8];
+#pragma unroll
+              for (int u = 0; u < 8; ++u) dk[u] = coop_dist(rv, cbq + static_cast<long long>(k0 + u) * D, lane);
+#pragma unroll
+              for (int u = 0; u < 8; ++u)
+                if (dk[u] < dbest) { dbest = dk[u]; best = k0 + u; }  // ascending k: first minimum kept
+            }
+          } else {
+            const int nb = dc.w & 7;
+            const double d0 = coop_dist(rv, cbq + static_cast<long long>(dc.x) * D, lane);
+            const double d1 = coop_dist(rv, cbq + static_cast<long long>(dc.y) * D, lane);
+            const double d2 = nb > 2 ? coop_dist(rv, cbq + static_cast<long long>(dc.z) * D, lane) : INFINITY;
+            dbest = d0;
+            best = dc.x;
+            if (d1 < dbest || (d1 == dbest && dc.y < best)) { dbest = d1; best = dc.y; }
+            if (nb > 2 && (d2 < dbest || (d2 == dbest && dc.z < best))) { dbest = d2; best = dc.z; }
+            int blk = -1;
+            if ((dc.x >> 5) == (dc.y >> 5)) blk = dc.x >> 5;
+            else if (nb > 2 && (dc.z >> 5) == (dc.x >> 5)) blk = dc.x >> 5;
+            else if (nb > 2 && (dc.z >> 5) == (dc.y >> 5)) blk = dc.y >> 5;
+            if (blk >= 0) {
+              // two band members share a 32-code block: a third could hide behind them -> score the block exactly
+              ++n_sub;
+              for (int k0 = blk * 32; k0 < blk * 32 + 32; k0 += 8) {
+                double dk[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) dk[u] = coop_dist(rv, cbq + static_cast<long long>(k0 + u) * D, lane);
+#pragma unroll
+                for (int u = 0; u < 8; ++u)
+                  if (dk[u] < dbest || (dk[u] == dbest && k0 + u < best)) { dbest = dk[u]; best = k0 + u; }
+              }
+            }
+          }
           ++n_ambig;
-          dbest = exact_dist(rrow, cbq + static_cast<long long>(i0) * D);
-          const double d1 = exact_dist(rrow, cbq + static_cast<long long>(i1) * D);
-          if (d1 < dbest || (d1 == dbest && i1 < best)) { dbest = d1; best = i1; }
-          if ((i0 >> 5) == (i1 >> 5)) conflict_blk = i0 >> 5;
-          if (in2) {
-            const double d2 = exact_dist(rrow, cbq + static_cast<long long>(i2) * D);
-            if (d2 < dbest || (d2 == dbest && i2 < best)) { dbest = d2; best = i2; }
-            if ((i2 >> 5) == (i0 >> 5)) conflict_blk = i0 >> 5;
-            else if ((i2 >> 5) == (i1 >> 5)) conflict_blk = i1 >> 5;
-          }
+          if (lane == 0) sel_s[r] = best;
         }
-        // rows with two band members in one 32-code block: the warp scores that block exactly, one code per lane
-        unsigned cmask = __ballot_sync(0xffffffffu, conflict_blk >= 0);
-        while (cmask) {
-          const int src = __ffs(cmask) - 1;
-          cmask &= cmask - 1;
-          const int blk = __shfl_sync(0xffffffffu, conflict_blk, src);
-          int k = blk * 32 + lane;
-          double dk = exact_dist(R + (quarter * 32 + src) * RSTRIDE, cbq + static_cast<long long>(k) * D);
-          warp_argmin(dk, k);
-          if (lane == src) {
-            ++n_sub;
-            if (dk < dbest || (dk == dbest && k < best)) { dbest = dk; best = k; }
-          }
-        }
-        // rows with four or more band members (rare): the warp scans the whole codebook exactly for that row
-        unsigned omask = __ballot_sync(0xffffffffu, overflow);
-        if (overflow) { ++n_ambig; ++n_full; }
-        while (omask) {
-          const int src = __ffs(omask) - 1;
-          omask &= omask - 1;
-          const float* rsrc = R + (quarter * 32 + src) * RSTRIDE;
-          double dmin = INFINITY;
-          int kmin = 0x7fffffff;
-          for (int k = lane; k < p.K; k += 32) {
-            const double dk = exact_dist(rsrc, cbq + static_cast<long long>(k) * D);
-            if (dk < dmin) { dmin = dk; kmin = k; }  // k ascending per lane: first minimum kept
-          }
-          warp_argmin(dmin, kmin);
-          if (lane == src) best = kmin;
-        }
-        sel_s[row] = best;
-        if (live) p.codes[f * p.Q + q] = best;
       }
       scan_barrier();
       // ---- residual update with the exact fp32 codeword (same op as the reference): warp w owns rows [16w, 16w+16),
@@ -362,7 +384,9 @@ __global__ void __launch_bounds__(320, 1) rvq_encode_kernel(const __grid_constan
       {
         const float* cbq = p.codebooks + static_cast<long long>(q) * p.K * D;
         for (int r = warp * 16; r < warp * 16 + 16; ++r) {
-          const float4 cw = __ldg(reinterpret_cast<const float4*>(cbq + static_cast<long long>(sel_s[r]) * D) + lane);
+          const int sel = sel_s[r];
+          if (lane == 0 && f0 + r < p.num_frames) p.codes[(f0 + r) * p.Q + q] = sel;
+          const float4 cw = __ldg(reinterpret_cast<const float4*>(cbq + static_cast<long long>(sel) * D) + lane);
           float4* dst = reinterpret_cast<float4*>(R + r * RSTRIDE) + lane;
           float4 v = *dst;
           v.x -= cw.x; v.y -= cw.y; v.z -= cw.z; v.w -= cw.w;
@@ -370,11 +394,13 @@ __global__ void __launch_bounds__(320, 1) rvq_encode_kernel(const __grid_constan
         }
       }
     }
-    if (p.stats != nullptr && half == 0 && live) {
-      atomicAdd(p.stats + 0, static_cast<unsigned long long>(p.Q));
-      if (n_ambig) atomicAdd(p.stats + 1, n_ambig);
-      if (n_full) atomicAdd(p.stats + 2, n_full);
-      if (n_sub) atomicAdd(p.stats + 3, n_sub);
+    if (p.stats != nullptr) {
+      if (half == 0 && live) atomicAdd(p.stats + 0, static_cast<unsigned long long>(p.Q));
+      if (lane == 0) {  // the cooperative decision counts per warp
+        if (n_ambig) atomicAdd(p.stats + 1, n_ambig);
+        if (n_full) atomicAdd(p.stats + 2, n_full);
+        if (n_sub) atomicAdd(p.stats + 3, n_sub);
+      }
     }
   }
 
