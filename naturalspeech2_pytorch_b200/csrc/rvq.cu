@@ -39,12 +39,11 @@ constexpr int MAX_K = 2048;
 constexpr int OFF_A = 0;
 constexpr int OFF_B = OFF_A + A_BYTES;
 constexpr int OFF_R = OFF_B + RING * B_BYTES;        // fp32 residuals, row-major padded: 67.6 KB
-constexpr int OFF_CN2 = OFF_R + BF * RSTRIDE * 4;    // ||c||^2 of the current stage
-constexpr int OFF_MERGE = OFF_CN2 + MAX_K * 4;       // top-4 keys of the second column half, per row
-constexpr int OFF_ROWP = OFF_MERGE + BF * 4 * 4;     // per-row {scale, dscale, margin, |r|^2}
+constexpr int OFF_CN2 = OFF_R + BF * RSTRIDE * 4;    // ||c||^2, double-buffered across stages (2 x 8 KB)
+constexpr int OFF_KEYS = OFF_CN2 + 2 * MAX_K * 4;    // top-8 keys of each column half: [half][row][8] floats (8 KB)
+constexpr int OFF_ROWP = OFF_KEYS + 2 * BF * 8 * 4;  // per-row {scale, dscale, E16, unused}
 constexpr int OFF_SEL = OFF_ROWP + BF * 4 * 4;       // chosen code per row (this stage)
-constexpr int OFF_DEC = OFF_SEL + BF * 4;            // per row {i0, i1, i2, band size | overflow << 3}
-constexpr int OFF_BAR = OFF_DEC + BF * 16;
+constexpr int OFF_BAR = OFF_SEL + BF * 4;
 constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
 constexpr int TMEM_COLS = 256;
 constexpr int SCAN_THREADS = 256;     // warps 0-7: quarter = warp & 3 (TMEM lanes), column half = warp >> 2
@@ -110,6 +109,18 @@ __device__ __forceinline__ void insert4(float key, float& g0, float& g1, float& 
   g3 = fminf(g3, t);
 }
 
+// same for an ascending 8-tuple: 15 min/max
+__device__ __forceinline__ void insert8(float key, float (&g)[8]) {
+  float t = key;
+#pragma unroll
+  for (int i = 0; i < 7; ++i) {
+    const float lo = fminf(g[i], t);
+    t = fmaxf(g[i], t);
+    g[i] = lo;
+  }
+  g[7] = fminf(g[7], t);
+}
+
 // (distance, index) lexicographic minimum across the warp
 __device__ __forceinline__ void warp_argmin(double& d, int& k) {
 #pragma unroll
@@ -130,10 +141,9 @@ __global__ void __launch_bounds__(320, 1) rvq_encode_kernel(const __grid_constan
                                              ~static_cast<uintptr_t>(1023));
   float* R = reinterpret_cast<float*>(smem + OFF_R);
   float* cn2_s = reinterpret_cast<float*>(smem + OFF_CN2);
-  float* merge_s = reinterpret_cast<float*>(smem + OFF_MERGE);
+  float* keys_s = reinterpret_cast<float*>(smem + OFF_KEYS);
   float4* rowp_s = reinterpret_cast<float4*>(smem + OFF_ROWP);
   int* sel_s = reinterpret_cast<int*>(smem + OFF_SEL);
-  int4* dec_s = reinterpret_cast<int4*>(smem + OFF_DEC);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
   uint64_t* b_full = bars + 0;    // [RING]
   uint64_t* b_empty = bars + 3;   // [RING]
@@ -213,43 +223,48 @@ __global__ void __launch_bounds__(320, 1) rvq_encode_kernel(const __grid_constan
     // ================================ scan threads ================================
     const int quarter = warp & 3, half = warp >> 2;
     const int row = quarter * 32 + lane;       // frame owned (together with the thread of the other half)
-    const long long f = f0 + row;
-    const bool live = f < p.num_frames;
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
     float* rrow = R + row * RSTRIDE;
 
-    // cooperative, coalesced load of the 128 frames: warp w fills rows [16w, 16w+16)
-    for (int r = warp * 16; r < warp * 16 + 16; ++r) {
-      const long long fr = f0 + r;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (fr < p.num_frames) v = __ldg(reinterpret_cast<const float4*>(p.frames + fr * D) + lane);
-      reinterpret_cast<float4*>(R + r * RSTRIDE)[lane] = v;
+    // per-row parameters of a stage from the row's residual held as 4 dims per lane (warp-cooperative)
+    auto publish_row_params = [&](int r, float4 v, float cmax, float cscale) {
+      float amax = fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w)));
+      float ss = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, v.w * v.w)));
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+        ss += __shfl_xor_sync(0xffffffffu, ss, o);
+      }
+      if (lane == 0) {
+        int ex = 0;
+        if (amax > 0.f) (void)frexpf(amax, &ex);          // amax = m * 2^ex, m in [0.5, 1)
+        const float xs = ldexpf(1.0f, -ex);               // exact power-of-two scale into fp16 range
+        const float dscale = -2.0f * ldexpf(cscale, ex);  // s~ = cn2 + dscale * dot'
+        // |s~_k - s_k| <= E16 = 2 * 1.05 * 2^-10 * ||r|| * max||c||  (fp16 operand rounding, fp32 accumulate);
+        // 1.002 covers the fp32 rounding of the reduced ||r||^2
+        const float e16 = 2.0f * 0.001026f * sqrtf(ss) * 1.002f * cmax;
+        rowp_s[r] = make_float4(xs, dscale, e16, ss);
+      }
+    };
+
+    // cooperative, coalesced load of the 128 frames: warp w fills rows [16w, 16w+16); stage-0 row parameters
+    {
+      const float cmax0 = __ldg(p.meta + 0), cscale0 = __ldg(p.meta + 1);
+      for (int r = warp * 16; r < warp * 16 + 16; ++r) {
+        const long long fr = f0 + r;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (fr < p.num_frames) v = __ldg(reinterpret_cast<const float4*>(p.frames + fr * D) + lane);
+        reinterpret_cast<float4*>(R + r * RSTRIDE)[lane] = v;
+        publish_row_params(r, v, cmax0, cscale0);
+      }
+      for (int i = threadIdx.x; i < p.K; i += SCAN_THREADS) cn2_s[i] = __ldg(p.cn2 + i);
     }
     unsigned long long n_ambig = 0, n_full = 0, n_sub = 0;
     uint32_t it = 0;
     for (int q = 0; q < p.Q; ++q) {
-      scan_barrier();  // residuals of this stage are in place (frame load / previous stage's update)
-      const float cmax = __ldg(p.meta + 2 * q), cscale = __ldg(p.meta + 2 * q + 1);
-      if (half == 0) {
-        // row scale (exact power of two into fp16 range), |r|^2, filter margin
-        float amax = 0.f, ss = 0.f;
-#pragma unroll 8
-        for (int i = 0; i < D / 4; ++i) {
-          const float4 v = reinterpret_cast<const float4*>(rrow)[i];
-          amax = fmaxf(fmaxf(amax, fabsf(v.x)), fmaxf(fabsf(v.y), fmaxf(fabsf(v.z), fabsf(v.w))));
-          ss = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, ss))));
-        }
-        int ex = 0;
-        if (amax > 0.f) (void)frexpf(amax, &ex);  // amax = m * 2^ex, m in [0.5, 1)
-        const float xs = ldexpf(1.0f, -ex);
-        const float dscale = -2.0f * ldexpf(cscale, ex);  // s~ = cn2 + dscale * dot'
-        // |s~_k - s_k| <= E16 = 2 * 1.05 * 2^-10 * ||r|| * max||c||  (fp16 operand rounding, fp32 accumulate)
-        const float e16 = 2.0f * 0.001026f * sqrtf(ss) * 1.001f * cmax;
-        rowp_s[row] = make_float4(xs, dscale, e16, ss);
-      }
-      for (int i = threadIdx.x; i < p.K; i += SCAN_THREADS) cn2_s[i] = __ldg(p.cn2 + q * p.K + i);
-      scan_barrier();
+      scan_barrier();  // [B1] residuals, row parameters and ||c||^2 of this stage are in place
       const float4 rp = rowp_s[row];
+      const float* cn2q = cn2_s + (q & 1) * MAX_K;
       // ---- fp16 A tile: this thread converts dims [64*half, 64*half + 64) of its row into atom `half` ----
       {
         const float xs = rp.x;
@@ -267,10 +282,21 @@ __global__ void __launch_bounds__(320, 1) rvq_encode_kernel(const __grid_constan
       }
       fence_proxy_async_smem();
       mbar_arrive(smem_u32(a_full));
+      // prefetch ||c||^2 of the next stage into registers (stored to the other buffer after the scan)
+      float cn_next[MAX_K / SCAN_THREADS];
+      if (q + 1 < p.Q) {
+#pragma unroll
+        for (int u = 0; u < MAX_K / SCAN_THREADS; ++u) {
+          const int i = threadIdx.x + u * SCAN_THREADS;
+          cn_next[u] = (i < p.K) ? __ldg(p.cn2 + (q + 1) * p.K + i) : 0.f;
+        }
+      }
 
-      // ---- scan this thread's 64 columns of every 128-code chunk: branch-free top-4 on packed keys ----
+      // ---- scan this thread's 64 columns of every 128-code chunk: branch-free top-8 on packed keys ----
       const float dscale = rp.y;
-      float g0 = INFINITY, g1 = INFINITY, g2 = INFINITY, g3 = INFINITY;
+      float g[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) g[i] = INFINITY;
       for (int c = 0; c < chunks; ++c, ++it) {
         const uint32_t buf = it & 1, dph = (it >> 1) & 1;
         mbar_wait(smem_u32(&d_full[buf]), dph);
@@ -281,7 +307,7 @@ __global__ void __launch_bounds__(320, 1) rvq_encode_kernel(const __grid_constan
           tmem_ld32(lane_addr + buf * BC + half * 64 + sub * 32, v);
           tmem_ld_wait();
           const int sub_id = c * 4 + half * 2 + sub;   // 32-code block index: code = sub_id * 32 + i
-          const float* cn = cn2_s + sub_id * 32;
+          const float* cn = cn2q + sub_id * 32;
           // local top-2 of the 32 scores, index i in the low 5 bits; two interleaved trackers for ILP
           float a0 = INFINITY, a1 = INFINITY, b0 = INFINITY, b1 = INFINITY;
 #pragma unroll
@@ -295,94 +321,122 @@ __global__ void __launch_bounds__(320, 1) rvq_encode_kernel(const __grid_constan
           }
           const float l0 = fminf(a0, b0);
           const float l1 = fminf(fmaxf(a0, b0), fminf(a1, b1));
-          // widen the index field to 11 bits (block id above the 5 local bits) and merge into the global top-4
+          // widen the index field to 11 bits (block id above the 5 local bits) and merge into the global top-8
           const uint32_t blk = static_cast<uint32_t>(sub_id) << 5;
-          insert4(__uint_as_float((__float_as_uint(l0) & 0xFFFFF81Fu) | blk), g0, g1, g2, g3);
-          insert4(__uint_as_float((__float_as_uint(l1) & 0xFFFFF81Fu) | blk), g0, g1, g2, g3);
+          insert8(__uint_as_float((__float_as_uint(l0) & 0xFFFFF81Fu) | blk), g);
+          insert8(__uint_as_float((__float_as_uint(l1) & 0xFFFFF81Fu) | blk), g);
         }
         tc_fence_before();
         mbar_arrive(smem_u32(&d_empty[buf]));
       }
-
-      // ---- merge the two column halves of each row ----
-      if (half == 1) *reinterpret_cast<float4*>(merge_s + row * 4) = make_float4(g0, g1, g2, g3);
-      scan_barrier();
-      if (half == 0) {
-        const float4 o = *reinterpret_cast<const float4*>(merge_s + row * 4);
-        insert4(o.x, g0, g1, g2, g3);
-        insert4(o.y, g0, g1, g2, g3);
-        insert4(o.z, g0, g1, g2, g3);
-        insert4(o.w, g0, g1, g2, g3);
-        // ---- classify: how many keys sit inside the error band of the best key ----
-        // Candidates = every code whose key is within the error band of the best key.  A band member can only be
-        // missing from (g0,g1,g2) if g3 is in the band too (-> full scan) or if it was 3rd+ inside its 32-code block,
-        // in which case two better band members share that block (-> that block is scanned exactly).
-        const float etrunc = 0.000244140625f * 1.01f * (fabsf(g0) + 2.0f * rp.z);  // 2^-12 relative key truncation
-        const float lim = g0 + 2.0f * (rp.z + etrunc);
-        const int i0 = __float_as_uint(g0) & 0x7FF, i1 = __float_as_uint(g1) & 0x7FF, i2 = __float_as_uint(g2) & 0x7FF;
-        const int nband = 1 + (g1 <= lim ? 1 : 0) + ((g1 <= lim && g2 <= lim) ? 1 : 0);
-        const int overflow = (g3 <= lim) ? 8 : 0;
-        dec_s[row] = make_int4(i0, i1, i2, nband | overflow);
-        sel_s[row] = i0;
-      }
-      scan_barrier();
-      // ---- exact decision, warp-cooperative: warp w owns rows [16w, 16w+16) ----
       {
-        const float* cbq = p.codebooks + static_cast<long long>(q) * p.K * D;
-        for (int r = warp * 16; r < warp * 16 + 16; ++r) {
-          const int4 dc = dec_s[r];
-          if ((dc.w & 15) == 1) continue;  // unique candidate: the filter's winner is exact
+        float4* kd = reinterpret_cast<float4*>(keys_s + (half * BF + row) * 8);
+        kd[0] = make_float4(g[0], g[1], g[2], g[3]);
+        kd[1] = make_float4(g[4], g[5], g[6], g[7]);
+      }
+      if (q + 1 < p.Q) {
+        float* cnw = cn2_s + ((q + 1) & 1) * MAX_K;
+#pragma unroll
+        for (int u = 0; u < MAX_K / SCAN_THREADS; ++u) {
+          const int i = threadIdx.x + u * SCAN_THREADS;
+          if (i < p.K) cnw[i] = cn_next[u];
+        }
+      }
+      scan_barrier();  // [B2] both halves' key lists are published
+
+      // ---- exact decision: warp w owns rows [16w, 16w+16) ----
+      // Candidates = every code whose key is within the error band of the best key.  A band member can only be
+      // missing from the merged top-8 if the 8th key is in the band too (-> exact scan of the whole codebook) or
+      // if it was 3rd+ inside its 32-code block, in which case two better band members share that block
+      // (-> that block is scanned exactly).
+      const float* cbq = p.codebooks + static_cast<long long>(q) * p.K * D;
+      {
+        // lanes 0..15: merge + classify one row each
+        int my_n = 1, my_blk = -1;
+        float m[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) m[i] = INFINITY;
+        const int myrow = warp * 16 + (lane & 15);
+        {
+          const float4* k0 = reinterpret_cast<const float4*>(keys_s + myrow * 8);
+          const float4* k1 = reinterpret_cast<const float4*>(keys_s + (BF + myrow) * 8);
+          const float4 x0 = k0[0], x1 = k0[1], y0 = k1[0], y1 = k1[1];
+          m[0] = x0.x; m[1] = x0.y; m[2] = x0.z; m[3] = x0.w; m[4] = x1.x; m[5] = x1.y; m[6] = x1.z; m[7] = x1.w;
+          insert8(y0.x, m); insert8(y0.y, m); insert8(y0.z, m); insert8(y0.w, m);
+          insert8(y1.x, m); insert8(y1.y, m); insert8(y1.z, m); insert8(y1.w, m);
+          const float e16 = rowp_s[myrow].z;
+          const float etrunc = 0.000244140625f * 1.01f * (fabsf(m[0]) + 2.0f * e16);  // 2^-12 key truncation
+          const float lim = m[0] + 2.0f * (e16 + etrunc);
+#pragma unroll
+          for (int i = 1; i < 8; ++i) my_n += (m[i] <= lim) ? 1 : 0;   // keys are sorted: band = prefix
+          bool multi = false;
+#pragma unroll
+          for (int i = 0; i < 7; ++i)
+#pragma unroll
+            for (int j = i + 1; j < 8; ++j)
+              if (j < my_n && ((__float_as_uint(m[i]) >> 5) & 63) == ((__float_as_uint(m[j]) >> 5) & 63)) {
+                const int b = (__float_as_uint(m[i]) >> 5) & 63;
+                multi = multi || (my_blk >= 0 && my_blk != b);
+                my_blk = b;
+              }
+          if (multi) my_n = 8;  // two different crowded blocks: fall back to the exact scan of the codebook
+          if (lane < 16) sel_s[myrow] = __float_as_uint(m[0]) & 0x7FF;
+        }
+        const unsigned need = __ballot_sync(0xffffffffu, lane < 16 && my_n > 1);
+        unsigned todo = need;
+        while (todo) {
+          const int src = __ffs(todo) - 1;
+          todo &= todo - 1;
+          const int r = warp * 16 + src;
+          const int nb = __shfl_sync(0xffffffffu, my_n, src);
+          const int blk = __shfl_sync(0xffffffffu, my_blk, src);
           const float4 rv = reinterpret_cast<const float4*>(R + r * RSTRIDE)[lane];
-          int best;
-          double dbest;
-          if (dc.w & 8) {
-            // four or more keys in the band (rare): exact scan of the whole codebook, 8 codes in flight
+          double dbest = INFINITY;
+          int best = 0x7fffffff;
+          ++n_ambig;
+          if (nb >= 8) {
+            // the whole tracked list is inside the band (astronomically rare): exact scan of the codebook
             ++n_full;
-            dbest = INFINITY;
-            best = 0;
             for (int k0 = 0; k0 < p.K; k0 += 8) {
               double dk[8];
 #pragma unroll
               for (int u = 0; u < 8; ++u) dk[u] = coop_dist(rv, cbq + static_cast<long long>(k0 + u) * D, lane);
 #pragma unroll
               for (int u = 0; u < 8; ++u)
-                if (dk[u] < dbest) { dbest = dk[u]; best = k0 + u; }  // ascending k: first minimum kept
+                if (dk[u] < dbest) { dbest = dk[u]; best = k0 + u; }
             }
           } else {
-            const int nb = dc.w & 7;
-            const double d0 = coop_dist(rv, cbq + static_cast<long long>(dc.x) * D, lane);
-            const double d1 = coop_dist(rv, cbq + static_cast<long long>(dc.y) * D, lane);
-            const double d2 = nb > 2 ? coop_dist(rv, cbq + static_cast<long long>(dc.z) * D, lane) : INFINITY;
-            dbest = d0;
-            best = dc.x;
-            if (d1 < dbest || (d1 == dbest && dc.y < best)) { dbest = d1; best = dc.y; }
-            if (nb > 2 && (d2 < dbest || (d2 == dbest && dc.z < best))) { dbest = d2; best = dc.z; }
-            int blk = -1;
-            if ((dc.x >> 5) == (dc.y >> 5)) blk = dc.x >> 5;
-            else if (nb > 2 && (dc.z >> 5) == (dc.x >> 5)) blk = dc.x >> 5;
-            else if (nb > 2 && (dc.z >> 5) == (dc.y >> 5)) blk = dc.y >> 5;
+            double dk[7];
+            int kk[7];
+#pragma unroll
+            for (int u = 0; u < 7; ++u) {
+              kk[u] = __shfl_sync(0xffffffffu, __float_as_uint(m[u]) & 0x7FF, src);
+              dk[u] = (u < nb) ? coop_dist(rv, cbq + static_cast<long long>(kk[u]) * D, lane) : INFINITY;
+            }
+#pragma unroll
+            for (int u = 0; u < 7; ++u)
+              if (u < nb && (dk[u] < dbest || (dk[u] == dbest && kk[u] < best))) { dbest = dk[u]; best = kk[u]; }
             if (blk >= 0) {
-              // two band members share a 32-code block: a third could hide behind them -> score the block exactly
               ++n_sub;
               for (int k0 = blk * 32; k0 < blk * 32 + 32; k0 += 8) {
-                double dk[8];
+                double d8[8];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) dk[u] = coop_dist(rv, cbq + static_cast<long long>(k0 + u) * D, lane);
+                for (int u = 0; u < 8; ++u) d8[u] = coop_dist(rv, cbq + static_cast<long long>(k0 + u) * D, lane);
 #pragma unroll
                 for (int u = 0; u < 8; ++u)
-                  if (dk[u] < dbest || (dk[u] == dbest && k0 + u < best)) { dbest = dk[u]; best = k0 + u; }
+                  if (d8[u] < dbest || (d8[u] == dbest && k0 + u < best)) { dbest = d8[u]; best = k0 + u; }
               }
             }
           }
-          ++n_ambig;
           if (lane == 0) sel_s[r] = best;
         }
       }
-      scan_barrier();
-      // ---- residual update with the exact fp32 codeword (same op as the reference): warp w owns rows [16w, 16w+16),
-      //      each codeword is fetched with one coalesced 512-byte load ----
+      __syncwarp();
+      // ---- residual update with the exact fp32 codeword (same op as the reference) for this warp's own 16 rows;
+      //      one coalesced 512-byte load per codeword; next stage's row parameters from the updated row ----
       {
-        const float* cbq = p.codebooks + static_cast<long long>(q) * p.K * D;
+        const float cmaxn = (q + 1 < p.Q) ? __ldg(p.meta + 2 * (q + 1)) : 0.f;
+        const float cscalen = (q + 1 < p.Q) ? __ldg(p.meta + 2 * (q + 1) + 1) : 1.f;
         for (int r = warp * 16; r < warp * 16 + 16; ++r) {
           const int sel = sel_s[r];
           if (lane == 0 && f0 + r < p.num_frames) p.codes[(f0 + r) * p.Q + q] = sel;
@@ -391,11 +445,12 @@ __global__ void __launch_bounds__(320, 1) rvq_encode_kernel(const __grid_constan
           float4 v = *dst;
           v.x -= cw.x; v.y -= cw.y; v.z -= cw.z; v.w -= cw.w;
           *dst = v;
+          if (q + 1 < p.Q) publish_row_params(r, v, cmaxn, cscalen);
         }
       }
     }
     if (p.stats != nullptr) {
-      if (half == 0 && live) atomicAdd(p.stats + 0, static_cast<unsigned long long>(p.Q));
+      if (half == 0 && f0 + row < p.num_frames) atomicAdd(p.stats + 0, static_cast<unsigned long long>(p.Q));
       if (lane == 0) {  // the cooperative decision counts per warp
         if (n_ambig) atomicAdd(p.stats + 1, n_ambig);
         if (n_full) atomicAdd(p.stats + 2, n_full);
