@@ -44,7 +44,7 @@ constexpr int OFF_KEYS = OFF_CN2 + 2 * MAX_K * 4;    // top-8 keys of each colum
 constexpr int OFF_ROWP = OFF_KEYS + 2 * BF * 8 * 4;  // per-row {scale, dscale, E16, unused}
 constexpr int OFF_SEL = OFF_ROWP + BF * 4 * 4;       // chosen code per row (this stage)
 constexpr int OFF_BAR = OFF_SEL + BF * 4;
-constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
+constexpr int SMEM_BYTES = OFF_BAR + 256;
 constexpr int TMEM_COLS = 256;
 constexpr int SCAN_THREADS = 256;     // warps 0-7: quarter = warp & 3 (TMEM lanes), column half = warp >> 2
 }  // namespace rvq
@@ -84,10 +84,13 @@ __device__ __forceinline__ double exact_dist(const float* rrow, const float* __r
   return (a0 + a1) + (a2 + a3);
 }
 
-// Warp-cooperative variant: lane l owns dims [4l, 4l+4); one coalesced 512-byte load of the codeword, a fixed
-// butterfly reduction (so equal inputs give bit-equal results).  Every lane returns the full distance.
-__device__ __forceinline__ double coop_dist(const float4 r, const float* __restrict__ c, int lane) {
-  const float4 v = __ldg(reinterpret_cast<const float4*>(c) + lane);
+// Warp-cooperative variant: lane l owns dims [4l, 4l+4); one coalesced 512-byte load of the codeword (issued by the
+// caller so that several are in flight), a fixed butterfly reduction (equal inputs give bit-equal results).
+// Every lane returns the full distance.
+__device__ __forceinline__ float4 coop_load(const float* __restrict__ c, int lane) {
+  return __ldg(reinterpret_cast<const float4*>(c) + lane);
+}
+__device__ __forceinline__ double coop_reduce(const float4 r, const float4 v) {
   const double d0 = static_cast<double>(r.x) - static_cast<double>(v.x);
   const double d1 = static_cast<double>(r.y) - static_cast<double>(v.y);
   const double d2 = static_cast<double>(r.z) - static_cast<double>(v.z);
@@ -136,9 +139,13 @@ __device__ __forceinline__ void warp_argmin(double& d, int& k) {
 // Low 11 bits = index (K <= 2048); the 2^-12 relative truncation is folded into the re-score margin.
 __global__ void __launch_bounds__(320, 1) rvq_encode_kernel(const __grid_constant__ RvqDev p) {
   using namespace rvq;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                             ~static_cast<uintptr_t>(1023));
+  // declared 1024-byte aligned (checked below) and indexed directly so the compiler keeps every access in the
+  // shared state space (LDS/STS instead of generic LD/ST)
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) {
+    printf("ns2 rvq: dynamic shared memory is not 1024-byte aligned\n");
+    __trap();
+  }
   float* R = reinterpret_cast<float*>(smem + OFF_R);
   float* cn2_s = reinterpret_cast<float*>(smem + OFF_CN2);
   float* keys_s = reinterpret_cast<float*>(smem + OFF_KEYS);
@@ -345,86 +352,105 @@ __global__ void __launch_bounds__(320, 1) rvq_encode_kernel(const __grid_constan
       scan_barrier();  // [B2] both halves' key lists are published
 
       // ---- exact decision: warp w owns rows [16w, 16w+16) ----
-      // Candidates = every code whose key is within the error band of the best key.  A band member can only be
-      // missing from the merged top-8 if the 8th key is in the band too (-> exact scan of the whole codebook) or
-      // if it was 3rd+ inside its 32-code block, in which case two better band members share that block
-      // (-> that block is scanned exactly).
+      // Candidates = every code whose key is within the error band of the best key.  Each column half keeps its own
+      // sorted top-8; a band member can only be missing from the two lists if a list is entirely inside the band
+      // (-> exact scan of the whole codebook) or if it was 3rd+ inside its 32-code block, in which case two better
+      // band members share that block (-> that block is scanned exactly).
       const float* cbq = p.codebooks + static_cast<long long>(q) * p.K * D;
       {
-        // lanes 0..15: merge + classify one row each
-        int my_n = 1, my_blk = -1;
-        float m[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) m[i] = INFINITY;
+        // lanes 0..15 classify one row each (lanes 16..31 mirror them): band sizes of the two sorted lists
         const int myrow = warp * 16 + (lane & 15);
+        float ka[8], kb[8];
         {
           const float4* k0 = reinterpret_cast<const float4*>(keys_s + myrow * 8);
           const float4* k1 = reinterpret_cast<const float4*>(keys_s + (BF + myrow) * 8);
           const float4 x0 = k0[0], x1 = k0[1], y0 = k1[0], y1 = k1[1];
-          m[0] = x0.x; m[1] = x0.y; m[2] = x0.z; m[3] = x0.w; m[4] = x1.x; m[5] = x1.y; m[6] = x1.z; m[7] = x1.w;
-          insert8(y0.x, m); insert8(y0.y, m); insert8(y0.z, m); insert8(y0.w, m);
-          insert8(y1.x, m); insert8(y1.y, m); insert8(y1.z, m); insert8(y1.w, m);
-          const float e16 = rowp_s[myrow].z;
-          const float etrunc = 0.000244140625f * 1.01f * (fabsf(m[0]) + 2.0f * e16);  // 2^-12 key truncation
-          const float lim = m[0] + 2.0f * (e16 + etrunc);
-#pragma unroll
-          for (int i = 1; i < 8; ++i) my_n += (m[i] <= lim) ? 1 : 0;   // keys are sorted: band = prefix
-          bool multi = false;
-#pragma unroll
-          for (int i = 0; i < 7; ++i)
-#pragma unroll
-            for (int j = i + 1; j < 8; ++j)
-              if (j < my_n && ((__float_as_uint(m[i]) >> 5) & 63) == ((__float_as_uint(m[j]) >> 5) & 63)) {
-                const int b = (__float_as_uint(m[i]) >> 5) & 63;
-                multi = multi || (my_blk >= 0 && my_blk != b);
-                my_blk = b;
-              }
-          if (multi) my_n = 8;  // two different crowded blocks: fall back to the exact scan of the codebook
-          if (lane < 16) sel_s[myrow] = __float_as_uint(m[0]) & 0x7FF;
+          ka[0] = x0.x; ka[1] = x0.y; ka[2] = x0.z; ka[3] = x0.w; ka[4] = x1.x; ka[5] = x1.y; ka[6] = x1.z; ka[7] = x1.w;
+          kb[0] = y0.x; kb[1] = y0.y; kb[2] = y0.z; kb[3] = y0.w; kb[4] = y1.x; kb[5] = y1.y; kb[6] = y1.z; kb[7] = y1.w;
         }
-        const unsigned need = __ballot_sync(0xffffffffu, lane < 16 && my_n > 1);
-        unsigned todo = need;
+        const float kmin = fminf(ka[0], kb[0]);
+        const float e16 = rowp_s[myrow].z;
+        const float etrunc = 0.000244140625f * 1.01f * (fabsf(kmin) + 2.0f * e16);  // 2^-12 key truncation
+        const float lim = kmin + 2.0f * (e16 + etrunc);
+        int na = 0, nb = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          na += (ka[i] <= lim) ? 1 : 0;   // lists are sorted: the band is a prefix
+          nb += (kb[i] <= lim) ? 1 : 0;
+        }
+        if (lane < 16) sel_s[myrow] = __float_as_uint(kmin) & 0x7FF;
+        unsigned todo = __ballot_sync(0xffffffffu, lane < 16 && na + nb > 1);
         while (todo) {
           const int src = __ffs(todo) - 1;
           todo &= todo - 1;
           const int r = warp * 16 + src;
-          const int nb = __shfl_sync(0xffffffffu, my_n, src);
-          const int blk = __shfl_sync(0xffffffffu, my_blk, src);
+          const int ca = __shfl_sync(0xffffffffu, na, src), cb = __shfl_sync(0xffffffffu, nb, src);
           const float4 rv = reinterpret_cast<const float4*>(R + r * RSTRIDE)[lane];
           double dbest = INFINITY;
           int best = 0x7fffffff;
           ++n_ambig;
-          if (nb >= 8) {
-            // the whole tracked list is inside the band (astronomically rare): exact scan of the codebook
+          // candidate indices of both lists (uniform across the warp after the shuffles)
+          int kk[16];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            kk[u] = __shfl_sync(0xffffffffu, __float_as_uint(ka[u]) & 0x7FF, src);
+            kk[8 + u] = __shfl_sync(0xffffffffu, __float_as_uint(kb[u]) & 0x7FF, src);
+          }
+          // crowded 32-code block? (blocks never span the two halves)
+          int blk = -1;
+          bool full = (ca >= 8) || (cb >= 8);
+#pragma unroll
+          for (int i = 0; i < 7; ++i)
+#pragma unroll
+            for (int j = i + 1; j < 8; ++j) {
+              if (j < ca && (kk[i] >> 5) == (kk[j] >> 5)) { full = full || (blk >= 0 && blk != (kk[i] >> 5)); blk = kk[i] >> 5; }
+              if (j < cb && (kk[8 + i] >> 5) == (kk[8 + j] >> 5)) {
+                full = full || (blk >= 0 && blk != (kk[8 + i] >> 5));
+                blk = kk[8 + i] >> 5;
+              }
+            }
+          if (full) {
+            // a whole list inside the band, or two crowded blocks (astronomically rare): exact scan of the codebook
             ++n_full;
             for (int k0 = 0; k0 < p.K; k0 += 8) {
-              double dk[8];
+              float4 cv[8];
 #pragma unroll
-              for (int u = 0; u < 8; ++u) dk[u] = coop_dist(rv, cbq + static_cast<long long>(k0 + u) * D, lane);
+              for (int u = 0; u < 8; ++u) cv[u] = coop_load(cbq + static_cast<long long>(k0 + u) * D, lane);
 #pragma unroll
-              for (int u = 0; u < 8; ++u)
-                if (dk[u] < dbest) { dbest = dk[u]; best = k0 + u; }
+              for (int u = 0; u < 8; ++u) {
+                const double dk = coop_reduce(rv, cv[u]);
+                if (dk < dbest) { dbest = dk; best = k0 + u; }
+              }
             }
           } else {
-            double dk[7];
-            int kk[7];
+            float4 cv[16];
 #pragma unroll
-            for (int u = 0; u < 7; ++u) {
-              kk[u] = __shfl_sync(0xffffffffu, __float_as_uint(m[u]) & 0x7FF, src);
-              dk[u] = (u < nb) ? coop_dist(rv, cbq + static_cast<long long>(kk[u]) * D, lane) : INFINITY;
+            for (int u = 0; u < 8; ++u) {
+              if (u < ca) cv[u] = coop_load(cbq + static_cast<long long>(kk[u]) * D, lane);
+              if (u < cb) cv[8 + u] = coop_load(cbq + static_cast<long long>(kk[8 + u]) * D, lane);
             }
 #pragma unroll
-            for (int u = 0; u < 7; ++u)
-              if (u < nb && (dk[u] < dbest || (dk[u] == dbest && kk[u] < best))) { dbest = dk[u]; best = kk[u]; }
+            for (int u = 0; u < 8; ++u) {
+              if (u < ca) {
+                const double dk = coop_reduce(rv, cv[u]);
+                if (dk < dbest || (dk == dbest && kk[u] < best)) { dbest = dk; best = kk[u]; }
+              }
+              if (u < cb) {
+                const double dk = coop_reduce(rv, cv[8 + u]);
+                if (dk < dbest || (dk == dbest && kk[8 + u] < best)) { dbest = dk; best = kk[8 + u]; }
+              }
+            }
             if (blk >= 0) {
               ++n_sub;
               for (int k0 = blk * 32; k0 < blk * 32 + 32; k0 += 8) {
-                double d8[8];
+                float4 c8[8];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) d8[u] = coop_dist(rv, cbq + static_cast<long long>(k0 + u) * D, lane);
+                for (int u = 0; u < 8; ++u) c8[u] = coop_load(cbq + static_cast<long long>(k0 + u) * D, lane);
 #pragma unroll
-                for (int u = 0; u < 8; ++u)
-                  if (d8[u] < dbest || (d8[u] == dbest && k0 + u < best)) { dbest = d8[u]; best = k0 + u; }
+                for (int u = 0; u < 8; ++u) {
+                  const double dk = coop_reduce(rv, c8[u]);
+                  if (dk < dbest || (dk == dbest && k0 + u < best)) { dbest = dk; best = k0 + u; }
+                }
               }
             }
           }
@@ -433,17 +459,24 @@ __global__ void __launch_bounds__(320, 1) rvq_encode_kernel(const __grid_constan
       }
       __syncwarp();
       // ---- residual update with the exact fp32 codeword (same op as the reference) for this warp's own 16 rows;
-      //      one coalesced 512-byte load per codeword; next stage's row parameters from the updated row ----
+      //      all 16 codewords are fetched first (coalesced 512-byte loads in flight together); next stage's row
+      //      parameters come from the updated row ----
       {
         const float cmaxn = (q + 1 < p.Q) ? __ldg(p.meta + 2 * (q + 1)) : 0.f;
         const float cscalen = (q + 1 < p.Q) ? __ldg(p.meta + 2 * (q + 1) + 1) : 1.f;
-        for (int r = warp * 16; r < warp * 16 + 16; ++r) {
-          const int sel = sel_s[r];
-          if (lane == 0 && f0 + r < p.num_frames) p.codes[(f0 + r) * p.Q + q] = sel;
-          const float4 cw = __ldg(reinterpret_cast<const float4*>(cbq + static_cast<long long>(sel) * D) + lane);
+        float4 cw[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+          const int sel = sel_s[warp * 16 + u];
+          cw[u] = coop_load(cbq + static_cast<long long>(sel) * D, lane);
+          if (lane == 0 && f0 + warp * 16 + u < p.num_frames) p.codes[(f0 + warp * 16 + u) * p.Q + q] = sel;
+        }
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+          const int r = warp * 16 + u;
           float4* dst = reinterpret_cast<float4*>(R + r * RSTRIDE) + lane;
           float4 v = *dst;
-          v.x -= cw.x; v.y -= cw.y; v.z -= cw.z; v.w -= cw.w;
+          v.x -= cw[u].x; v.y -= cw[u].y; v.z -= cw[u].z; v.w -= cw[u].w;
           *dst = v;
           if (q + 1 < p.Q) publish_row_params(r, v, cmaxn, cscalen);
         }
