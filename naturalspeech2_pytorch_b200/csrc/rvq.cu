@@ -43,7 +43,8 @@ constexpr int OFF_CN2 = OFF_R + BF * RSTRIDE * 4;    // ||c||^2, double-buffered
 constexpr int OFF_KEYS = OFF_CN2 + 2 * MAX_K * 4;    // top-8 keys of each column half: [half][row][8] floats (8 KB)
 constexpr int OFF_ROWP = OFF_KEYS + 2 * BF * 8 * 4;  // per-row {scale, dscale, E16, unused}
 constexpr int OFF_SEL = OFF_ROWP + BF * 4 * 4;       // chosen code per row (this stage)
-constexpr int OFF_BAR = OFF_SEL + BF * 4;
+constexpr int OFF_CAND = OFF_SEL + BF * 4;           // per-warp candidate list of the row being re-scored
+constexpr int OFF_BAR = OFF_CAND + 8 * 16 * 4;
 constexpr int SMEM_BYTES = OFF_BAR + 256;
 constexpr int TMEM_COLS = 256;
 constexpr int SCAN_THREADS = 256;     // warps 0-7: quarter = warp & 3 (TMEM lanes), column half = warp >> 2
@@ -151,6 +152,7 @@ __global__ void __launch_bounds__(320, 1) rvq_encode_kernel(const __grid_constan
   float* keys_s = reinterpret_cast<float*>(smem + OFF_KEYS);
   float4* rowp_s = reinterpret_cast<float4*>(smem + OFF_ROWP);
   int* sel_s = reinterpret_cast<int*>(smem + OFF_SEL);
+  int* cand_s = reinterpret_cast<int*>(smem + OFF_CAND);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
   uint64_t* b_full = bars + 0;    // [RING]
   uint64_t* b_empty = bars + 3;   // [RING]
@@ -257,6 +259,7 @@ __global__ void __launch_bounds__(320, 1) rvq_encode_kernel(const __grid_constan
     // cooperative, coalesced load of the 128 frames: warp w fills rows [16w, 16w+16); stage-0 row parameters
     {
       const float cmax0 = __ldg(p.meta + 0), cscale0 = __ldg(p.meta + 1);
+#pragma unroll 1
       for (int r = warp * 16; r < warp * 16 + 16; ++r) {
         const long long fr = f0 + r;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -380,38 +383,45 @@ __global__ void __launch_bounds__(320, 1) rvq_encode_kernel(const __grid_constan
         }
         if (lane < 16) sel_s[myrow] = __float_as_uint(kmin) & 0x7FF;
         unsigned todo = __ballot_sync(0xffffffffu, lane < 16 && na + nb > 1);
+        int* cand = cand_s + warp * 16;
+#pragma unroll 1
         while (todo) {
           const int src = __ffs(todo) - 1;
           todo &= todo - 1;
           const int r = warp * 16 + src;
           const int ca = __shfl_sync(0xffffffffu, na, src), cb = __shfl_sync(0xffffffffu, nb, src);
+          // the row's owner publishes its candidate indices: list a in cand[0..8), list b in cand[8..16)
+          if (lane == src) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              cand[u] = __float_as_uint(ka[u]) & 0x7FF;
+              cand[8 + u] = __float_as_uint(kb[u]) & 0x7FF;
+            }
+          }
+          __syncwarp();
           const float4 rv = reinterpret_cast<const float4*>(R + r * RSTRIDE)[lane];
           double dbest = INFINITY;
           int best = 0x7fffffff;
           ++n_ambig;
-          // candidate indices of both lists (uniform across the warp after the shuffles)
-          int kk[16];
-#pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            kk[u] = __shfl_sync(0xffffffffu, __float_as_uint(ka[u]) & 0x7FF, src);
-            kk[8 + u] = __shfl_sync(0xffffffffu, __float_as_uint(kb[u]) & 0x7FF, src);
-          }
-          // crowded 32-code block? (blocks never span the two halves)
+          // crowded 32-code block among the band members of one list? (blocks never span the two halves)
           int blk = -1;
           bool full = (ca >= 8) || (cb >= 8);
-#pragma unroll
-          for (int i = 0; i < 7; ++i)
-#pragma unroll
-            for (int j = i + 1; j < 8; ++j) {
-              if (j < ca && (kk[i] >> 5) == (kk[j] >> 5)) { full = full || (blk >= 0 && blk != (kk[i] >> 5)); blk = kk[i] >> 5; }
-              if (j < cb && (kk[8 + i] >> 5) == (kk[8 + j] >> 5)) {
-                full = full || (blk >= 0 && blk != (kk[8 + i] >> 5));
-                blk = kk[8 + i] >> 5;
-              }
-            }
+#pragma unroll 1
+          for (int l = 0; l < 2; ++l) {
+            const int cnt = l ? cb : ca;
+#pragma unroll 1
+            for (int i = 0; i + 1 < cnt; ++i)
+#pragma unroll 1
+              for (int j = i + 1; j < cnt; ++j)
+                if ((cand[8 * l + i] >> 5) == (cand[8 * l + j] >> 5)) {
+                  full = full || (blk >= 0 && blk != (cand[8 * l + i] >> 5));
+                  blk = cand[8 * l + i] >> 5;
+                }
+          }
           if (full) {
             // a whole list inside the band, or two crowded blocks (astronomically rare): exact scan of the codebook
             ++n_full;
+#pragma unroll 1
             for (int k0 = 0; k0 < p.K; k0 += 8) {
               float4 cv[8];
 #pragma unroll
@@ -423,25 +433,27 @@ __global__ void __launch_bounds__(320, 1) rvq_encode_kernel(const __grid_constan
               }
             }
           } else {
-            float4 cv[16];
+            // band members of both lists, four codewords in flight at a time
+            const int total = ca + cb;
+#pragma unroll 1
+            for (int u0 = 0; u0 < total; u0 += 4) {
+              float4 cv[4];
+              int kx[4];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-              if (u < ca) cv[u] = coop_load(cbq + static_cast<long long>(kk[u]) * D, lane);
-              if (u < cb) cv[8 + u] = coop_load(cbq + static_cast<long long>(kk[8 + u]) * D, lane);
-            }
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-              if (u < ca) {
-                const double dk = coop_reduce(rv, cv[u]);
-                if (dk < dbest || (dk == dbest && kk[u] < best)) { dbest = dk; best = kk[u]; }
+              for (int u = 0; u < 4; ++u) {
+                const int t = u0 + u;
+                kx[u] = (t < total) ? cand[t < ca ? t : 8 + (t - ca)] : cand[0];
+                cv[u] = coop_load(cbq + static_cast<long long>(kx[u]) * D, lane);
               }
-              if (u < cb) {
-                const double dk = coop_reduce(rv, cv[8 + u]);
-                if (dk < dbest || (dk == dbest && kk[8 + u] < best)) { dbest = dk; best = kk[8 + u]; }
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const double dk = coop_reduce(rv, cv[u]);
+                if (u0 + u < total && (dk < dbest || (dk == dbest && kx[u] < best))) { dbest = dk; best = kx[u]; }
               }
             }
             if (blk >= 0) {
               ++n_sub;
+#pragma unroll 1
               for (int k0 = blk * 32; k0 < blk * 32 + 32; k0 += 8) {
                 float4 c8[8];
 #pragma unroll
@@ -455,30 +467,35 @@ __global__ void __launch_bounds__(320, 1) rvq_encode_kernel(const __grid_constan
             }
           }
           if (lane == 0) sel_s[r] = best;
+          __syncwarp();
         }
       }
       __syncwarp();
       // ---- residual update with the exact fp32 codeword (same op as the reference) for this warp's own 16 rows;
-      //      all 16 codewords are fetched first (coalesced 512-byte loads in flight together); next stage's row
-      //      parameters come from the updated row ----
+      //      four coalesced 512-byte codeword loads in flight; next stage's row parameters from the updated row ----
       {
         const float cmaxn = (q + 1 < p.Q) ? __ldg(p.meta + 2 * (q + 1)) : 0.f;
         const float cscalen = (q + 1 < p.Q) ? __ldg(p.meta + 2 * (q + 1) + 1) : 1.f;
-        float4 cw[16];
+#pragma unroll 1
+        for (int u0 = 0; u0 < 16; u0 += 4) {
+          float4 cw[4];
 #pragma unroll
-        for (int u = 0; u < 16; ++u) {
-          const int sel = sel_s[warp * 16 + u];
-          cw[u] = coop_load(cbq + static_cast<long long>(sel) * D, lane);
-          if (lane == 0 && f0 + warp * 16 + u < p.num_frames) p.codes[(f0 + warp * 16 + u) * p.Q + q] = sel;
-        }
-#pragma unroll
-        for (int u = 0; u < 16; ++u) {
-          const int r = warp * 16 + u;
-          float4* dst = reinterpret_cast<float4*>(R + r * RSTRIDE) + lane;
-          float4 v = *dst;
-          v.x -= cw[u].x; v.y -= cw[u].y; v.z -= cw[u].z; v.w -= cw[u].w;
-          *dst = v;
-          if (q + 1 < p.Q) publish_row_params(r, v, cmaxn, cscalen);
+          for (int u = 0; u < 4; ++u) {
+            const int r = warp * 16 + u0 + u;
+            const int sel = sel_s[r];
+            cw[u] = coop_load(cbq + static_cast<long long>(sel) * D, lane);
+            if (lane == 0 && f0 + r < p.num_frames) p.codes[(f0 + r) * p.Q + q] = sel;
+          }
+#pragma unroll 1
+          for (int u = 0; u < 4; ++u) {
+            const int r = warp * 16 + u0 + u;
+            float4* dst = reinterpret_cast<float4*>(R + r * RSTRIDE) + lane;
+            float4 v = *dst;
+            const float4 c = (u == 0) ? cw[0] : (u == 1) ? cw[1] : (u == 2) ? cw[2] : cw[3];
+            v.x -= c.x; v.y -= c.y; v.z -= c.z; v.w -= c.w;
+            *dst = v;
+            if (q + 1 < p.Q) publish_row_params(r, v, cmaxn, cscalen);
+          }
         }
       }
     }
