@@ -181,21 +181,33 @@ __global__ void __launch_bounds__(192, 2) attn_fwd_kernel(const __grid_constant_
       tc_fence_after();
       const int valid = p.kv_len - j * BKV;  // columns >= valid are padding keys
       const bool full = valid >= BKV;
-      // pass 1: row maximum of the raw scores
-      float m_tile = -INFINITY;
+      // pass 1: row maximum of the raw scores (64 columns per TMEM round trip, 4 independent max chains)
+      float m_tile;
+      {
+        float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
 #pragma unroll 1
-      for (int cc = 0; cc < BKV / 32; ++cc) {
-        uint32_t r[32];
-        tmem_ld32(lane_addr + TM_S + cc * 32, r);
-        tmem_ld_wait();
-        if (full) {
+        for (int cc = 0; cc < BKV / 64; ++cc) {
+          uint32_t r0[32], r1[32];
+          tmem_ld32(lane_addr + TM_S + cc * 64, r0);
+          tmem_ld32(lane_addr + TM_S + cc * 64 + 32, r1);
+          tmem_ld_wait();
+          if (full) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) m_tile = fmaxf(m_tile, __uint_as_float(r[i]));
-        } else {
+            for (int i = 0; i < 32; i += 2) {
+              m0 = fmaxf(m0, __uint_as_float(r0[i]));
+              m1 = fmaxf(m1, __uint_as_float(r0[i + 1]));
+              m2 = fmaxf(m2, __uint_as_float(r1[i]));
+              m3 = fmaxf(m3, __uint_as_float(r1[i + 1]));
+            }
+          } else {
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (cc * 32 + i < valid) m_tile = fmaxf(m_tile, __uint_as_float(r[i]));
+            for (int i = 0; i < 32; ++i) {
+              if (cc * 64 + i < valid) m0 = fmaxf(m0, __uint_as_float(r0[i]));
+              if (cc * 64 + 32 + i < valid) m1 = fmaxf(m1, __uint_as_float(r1[i]));
+            }
+          }
         }
+        m_tile = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
       }
       const float m_new = fmaxf(m_run, m_tile * c);
       const float a = ex2_approx(m_run - m_new);  // 0 on the first tile (m_run = -inf)
@@ -204,41 +216,48 @@ __global__ void __launch_bounds__(192, 2) attn_fwd_kernel(const __grid_constant_
         mbar_wait(smem_u32(&o_full[(j - 1) & 1]), ((j - 1) >> 1) & 1);
         tc_fence_after();
       }
-      // pass 2: probabilities -> bf16 -> swizzled smem; row sum in fp32
-      float l_tile = 0.f;
+      // pass 2: probabilities -> bf16 -> swizzled smem; row sum in fp32 (4 independent chains)
+      float l_tile;
+      {
+        float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
 #pragma unroll 1
-      for (int cc = 0; cc < BKV / 32; ++cc) {
-        uint32_t r[32];
-        tmem_ld32(lane_addr + TM_S + cc * 32, r);
-        tmem_ld_wait();
-        uint32_t pk[16];
-        if (full) {
+        for (int cc = 0; cc < BKV / 32; ++cc) {
+          uint32_t r[32];
+          tmem_ld32(lane_addr + TM_S + cc * 32, r);
+          tmem_ld_wait();
+          uint32_t pk[16];
+          if (full) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float p0 = ex2_approx(fmaf(__uint_as_float(r[2 * i]), c, -m_new));
-            const float p1 = ex2_approx(fmaf(__uint_as_float(r[2 * i + 1]), c, -m_new));
-            l_tile += p0 + p1;
-            pk[i] = pack_bf16x2(p0, p1);
+            for (int i = 0; i < 16; i += 2) {
+              const float p0 = ex2_approx(fmaf(__uint_as_float(r[2 * i]), c, -m_new));
+              const float p1 = ex2_approx(fmaf(__uint_as_float(r[2 * i + 1]), c, -m_new));
+              const float p2 = ex2_approx(fmaf(__uint_as_float(r[2 * i + 2]), c, -m_new));
+              const float p3 = ex2_approx(fmaf(__uint_as_float(r[2 * i + 3]), c, -m_new));
+              l0 += p0; l1 += p1; l2 += p2; l3 += p3;
+              pk[i] = pack_bf16x2(p0, p1);
+              pk[i + 1] = pack_bf16x2(p2, p3);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const int c0 = cc * 32 + 2 * i;
+              const float p0 = (c0 < valid) ? ex2_approx(fmaf(__uint_as_float(r[2 * i]), c, -m_new)) : 0.f;
+              const float p1 =
+                  (c0 + 1 < valid) ? ex2_approx(fmaf(__uint_as_float(r[2 * i + 1]), c, -m_new)) : 0.f;
+              l0 += p0; l1 += p1;
+              pk[i] = pack_bf16x2(p0, p1);
+            }
           }
-        } else {
+          // 32 columns = 4 chunks of 16 bytes; chunk index within the 64-key atom is XOR-swizzled with row&7
+          uint8_t* atom = prow + (cc >> 1) * (BQ * 128);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const int c0 = cc * 32 + 2 * i;
-            const float p0 = (c0 < valid) ? ex2_approx(fmaf(__uint_as_float(r[2 * i]), c, -m_new)) : 0.f;
-            const float p1 =
-                (c0 + 1 < valid) ? ex2_approx(fmaf(__uint_as_float(r[2 * i + 1]), c, -m_new)) : 0.f;
-            l_tile += p0 + p1;
-            pk[i] = pack_bf16x2(p0, p1);
+          for (int q = 0; q < 4; ++q) {
+            const int chunk = (cc & 1) * 4 + q;
+            *reinterpret_cast<uint4*>(atom + ((chunk ^ (row & 7)) << 4)) =
+                make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
           }
         }
-        // 32 columns = 4 chunks of 16 bytes; chunk index within the 64-key atom is XOR-swizzled with row&7
-        uint8_t* atom = prow + (cc >> 1) * (BQ * 128);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int chunk = (cc & 1) * 4 + q;
-          *reinterpret_cast<uint4*>(atom + ((chunk ^ (row & 7)) << 4)) =
-              make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
-        }
+        l_tile = (l0 + l1) + (l2 + l3);
       }
       l_run = fmaf(l_run, a, l_tile);
       m_run = m_new;

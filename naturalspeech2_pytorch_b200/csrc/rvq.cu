@@ -235,46 +235,43 @@ __global__ void __launch_bounds__(320, 1) rvq_encode_kernel(const __grid_constan
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
     float* rrow = R + row * RSTRIDE;
 
-    // per-row parameters of a stage from the row's residual held as 4 dims per lane (warp-cooperative)
-    auto publish_row_params = [&](int r, float4 v, float cmax, float cscale) {
-      float amax = fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w)));
-      float ss = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, v.w * v.w)));
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
-        ss += __shfl_xor_sync(0xffffffffu, ss, o);
-      }
-      if (lane == 0) {
-        int ex = 0;
-        if (amax > 0.f) (void)frexpf(amax, &ex);          // amax = m * 2^ex, m in [0.5, 1)
-        const float xs = ldexpf(1.0f, -ex);               // exact power-of-two scale into fp16 range
-        const float dscale = -2.0f * ldexpf(cscale, ex);  // s~ = cn2 + dscale * dot'
-        // |s~_k - s_k| <= E16 = 2 * 1.05 * 2^-10 * ||r|| * max||c||  (fp16 operand rounding, fp32 accumulate);
-        // 1.002 covers the fp32 rounding of the reduced ||r||^2
-        const float e16 = 2.0f * 0.001026f * sqrtf(ss) * 1.002f * cmax;
-        rowp_s[r] = make_float4(xs, dscale, e16, ss);
-      }
-    };
-
     // cooperative, coalesced load of the 128 frames: warp w fills rows [16w, 16w+16); stage-0 row parameters
     {
-      const float cmax0 = __ldg(p.meta + 0), cscale0 = __ldg(p.meta + 1);
-#pragma unroll 1
+#pragma unroll 4
       for (int r = warp * 16; r < warp * 16 + 16; ++r) {
         const long long fr = f0 + r;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (fr < p.num_frames) v = __ldg(reinterpret_cast<const float4*>(p.frames + fr * D) + lane);
         reinterpret_cast<float4*>(R + r * RSTRIDE)[lane] = v;
-        publish_row_params(r, v, cmax0, cscale0);
       }
       for (int i = threadIdx.x; i < p.K; i += SCAN_THREADS) cn2_s[i] = __ldg(p.cn2 + i);
     }
     unsigned long long n_ambig = 0, n_full = 0, n_sub = 0;
     uint32_t it = 0;
     for (int q = 0; q < p.Q; ++q) {
-      scan_barrier();  // [B1] residuals, row parameters and ||c||^2 of this stage are in place
-      const float4 rp = rowp_s[row];
+      scan_barrier();  // [B1] residuals and ||c||^2 of this stage are in place
       const float* cn2q = cn2_s + (q & 1) * MAX_K;
+      // row scale (exact power of two into fp16 range), |r|^2 and the filter margin; both threads of a row compute
+      // them redundantly from the same data in the same order (bit-identical), so no exchange is needed
+      float4 rp;
+      {
+        const float cmax = __ldg(p.meta + 2 * q), cscale = __ldg(p.meta + 2 * q + 1);
+        float amax = 0.f, ss = 0.f;
+#pragma unroll 8
+        for (int i = 0; i < D / 4; ++i) {
+          const float4 v = reinterpret_cast<const float4*>(rrow)[i];
+          amax = fmaxf(fmaxf(amax, fabsf(v.x)), fmaxf(fabsf(v.y), fmaxf(fabsf(v.z), fabsf(v.w))));
+          ss = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, ss))));
+        }
+        int ex = 0;
+        if (amax > 0.f) (void)frexpf(amax, &ex);          // amax = m * 2^ex, m in [0.5, 1)
+        const float xs = ldexpf(1.0f, -ex);
+        const float dscale = -2.0f * ldexpf(cscale, ex);  // s~ = cn2 + dscale * dot'
+        // |s~_k - s_k| <= E16 = 2 * 1.05 * 2^-10 * ||r|| * max||c||  (fp16 operand rounding, fp32 accumulate)
+        const float e16 = 2.0f * 0.001026f * sqrtf(ss) * 1.001f * cmax;
+        rp = make_float4(xs, dscale, e16, ss);
+        if (half == 0) rowp_s[row] = rp;   // read by the decision warps after [B2]
+      }
       // ---- fp16 A tile: this thread converts dims [64*half, 64*half + 64) of its row into atom `half` ----
       {
         const float xs = rp.x;
@@ -472,29 +469,24 @@ __global__ void __launch_bounds__(320, 1) rvq_encode_kernel(const __grid_constan
       }
       __syncwarp();
       // ---- residual update with the exact fp32 codeword (same op as the reference) for this warp's own 16 rows;
-      //      four coalesced 512-byte codeword loads in flight; next stage's row parameters from the updated row ----
+      //      eight coalesced 512-byte codeword loads in flight ----
       {
-        const float cmaxn = (q + 1 < p.Q) ? __ldg(p.meta + 2 * (q + 1)) : 0.f;
-        const float cscalen = (q + 1 < p.Q) ? __ldg(p.meta + 2 * (q + 1) + 1) : 1.f;
 #pragma unroll 1
-        for (int u0 = 0; u0 < 16; u0 += 4) {
-          float4 cw[4];
+        for (int u0 = 0; u0 < 16; u0 += 8) {
+          float4 cw[8];
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
+          for (int u = 0; u < 8; ++u) {
             const int r = warp * 16 + u0 + u;
             const int sel = sel_s[r];
             cw[u] = coop_load(cbq + static_cast<long long>(sel) * D, lane);
             if (lane == 0 && f0 + r < p.num_frames) p.codes[(f0 + r) * p.Q + q] = sel;
           }
-#pragma unroll 1
-          for (int u = 0; u < 4; ++u) {
-            const int r = warp * 16 + u0 + u;
-            float4* dst = reinterpret_cast<float4*>(R + r * RSTRIDE) + lane;
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            float4* dst = reinterpret_cast<float4*>(R + (warp * 16 + u0 + u) * RSTRIDE) + lane;
             float4 v = *dst;
-            const float4 c = (u == 0) ? cw[0] : (u == 1) ? cw[1] : (u == 2) ? cw[2] : cw[3];
-            v.x -= c.x; v.y -= c.y; v.z -= c.z; v.w -= c.w;
+            v.x -= cw[u].x; v.y -= cw[u].y; v.z -= cw[u].z; v.w -= cw[u].w;
             *dst = v;
-            if (q + 1 < p.Q) publish_row_params(r, v, cmaxn, cscalen);
           }
         }
       }
