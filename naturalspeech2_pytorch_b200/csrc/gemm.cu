@@ -12,8 +12,7 @@
 //   warp 1     tcgen05.mma issuer (one elected lane; leader CTA only in the pair kernel), accumulators in TMEM,
 //              double-buffered across tiles
 //   warp 2     TMEM allocator
-//   warps 4-7  epilogue (4-11 in the pair kernel: two warps per TMEM lane quarter take alternate column chunks):
-//              tcgen05.ld -> registers -> bias / residual / GEGLU / FiLM+gate -> global
+//   warps 4-7  epilogue: tcgen05.ld -> registers -> bias / residual / GEGLU / FiLM+gate -> global
 // Three pipelines: smem ring (full/empty mbarriers, TMA <-> MMA), TMEM double buffer (tmem_full/empty,
 // MMA <-> epilogue), static round-robin tile scheduler (n fastest so co-resident CTAs share A rows in L2).
 //
@@ -250,15 +249,14 @@ __device__ __forceinline__ void epilogue_tile(const GemmDev& p, const TileCoord&
 constexpr int STG_BYTES = 32 * 128;  // one box: 32 rows x 128 bytes
 
 struct Stager {
-  uint32_t base;      // smem address of this warp's staging box
+  uint32_t base;      // smem address of this warp's two staging boxes
   uint32_t count;     // boxes issued so far
   int lane;
-  int slot;           // 0/1: which of the two warps sharing a TMEM lane quarter (they take alternate chunks)
   __device__ __forceinline__ uint32_t acquire() {
-    // the previous store from this box must have been read out by the TMA engine
-    if (lane == 0) tma_store_wait_read<0>();
+    // the box used two stores ago must have been read out by the TMA engine
+    if (lane == 0) tma_store_wait_read<1>();
     __syncwarp();
-    return base;
+    return base + (count & 1) * STG_BYTES;
   }
   // thread writes 16-byte piece j (0..7) of its 128-byte row
   __device__ __forceinline__ void put(uint32_t box, int j, uint4 v) const {
@@ -298,7 +296,7 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmDev& p, const TileCo
   const int tile_col0 = t.n_tile * BN;
   if constexpr (EPI == NS2_EPI_BF16) {
 #pragma unroll 1
-    for (int oc = st.slot * 64; oc < BN; oc += 128) {
+    for (int oc = 0; oc < BN; oc += 64) {
       if (tile_col0 + oc >= p.n) break;
       const uint32_t box = st.acquire();
 #pragma unroll
@@ -312,7 +310,7 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmDev& p, const TileCo
     }
   } else if constexpr (EPI == NS2_EPI_F32) {
 #pragma unroll 1
-    for (int oc = st.slot * 32; oc < BN; oc += 64) {
+    for (int oc = 0; oc < BN; oc += 32) {
       if (tile_col0 + oc >= p.n) break;
       const uint32_t box = st.acquire();
       float v[32];
@@ -327,7 +325,7 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmDev& p, const TileCo
   } else if constexpr (EPI == NS2_EPI_GEGLU) {
     static_assert(EPI != NS2_EPI_GEGLU || BN == 256, "GEGLU tiles pair 128 value + 128 gate rows");
 #pragma unroll 1
-    for (int oc = st.slot * 64; oc < 128; oc += 128) {  // output columns of this tile (one 64-column chunk per warp)
+    for (int oc = 0; oc < 128; oc += 64) {  // output columns of this tile
       const uint32_t box = st.acquire();
 #pragma unroll 1
       for (int h = 0; h < 2; ++h) {
@@ -355,7 +353,7 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmDev& p, const TileCo
   } else {  // NS2_EPI_WAVENET
     static_assert(EPI != NS2_EPI_WAVENET || NACC == 2, "wavenet block needs conv + res accumulators");
 #pragma unroll 1
-    for (int oc = st.slot * 64; oc < BN; oc += 128) {
+    for (int oc = 0; oc < BN; oc += 64) {
       if (tile_col0 + oc >= p.n) break;
       const uint32_t box = st.acquire();
 #pragma unroll 1
@@ -544,7 +542,7 @@ struct Gemm2Cfg {
   static constexpr int A_BYTES = BM * BK * 2;            // this CTA's 128 rows
   static constexpr int B_BYTES = (BN / 2) * BK * 2;      // this CTA's half of the B tile
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;  // multiple of 1024 for BN in {128, 176, 256}
-  static constexpr int STG_TOTAL = 8 * STG_BYTES;        // 8 epilogue warps x 1 staging box
+  static constexpr int STG_TOTAL = 4 * 2 * STG_BYTES;    // 4 epilogue warps x 2 staging boxes
   static constexpr int STAGES = (192 * 1024) / STAGE_BYTES > 8 ? 8 : (192 * 1024) / STAGE_BYTES;
   static constexpr int ACC_COLS = BN * NACC;
   static constexpr int ACC_STRIDE = (ACC_COLS <= 128) ? 128 : 256;  // column offset of the second stage
@@ -557,7 +555,7 @@ struct Gemm2Cfg {
 };
 
 template <int BN, int NACC, int EPI>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
     gemm2_kernel(const __grid_constant__ GemmDev p) {
   using Cfg = Gemm2Cfg<BN, NACC>;
   extern __shared__ uint8_t smem_raw[];
@@ -568,7 +566,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
   uint64_t* full_bar = bars;                          // [STAGES]  used in the leader CTA only
   uint64_t* empty_bar = bars + Cfg::STAGES;           // [STAGES]  one per CTA, signalled by multicast commit
   uint64_t* tfull_bar = bars + 2 * Cfg::STAGES;       // [2]       one per CTA, multicast commit
-  uint64_t* tempty_bar = bars + 2 * Cfg::STAGES + 2;  // [2]       leader only: 16 arrivals (8 warps x 2 CTAs)
+  uint64_t* tempty_bar = bars + 2 * Cfg::STAGES + 2;  // [2]       leader only: 8 arrivals (4 warps x 2 CTAs)
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::STAGES + 4);
 
   const int warp = threadIdx.x >> 5;
@@ -590,7 +588,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(smem_u32(&tfull_bar[i]), 1);
-      mbar_init(smem_u32(&tempty_bar[i]), 16);  // 8 epilogue warps x 2 CTAs
+      mbar_init(smem_u32(&tempty_bar[i]), 8);
     }
     fence_barrier_init();
   }
@@ -675,12 +673,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
     }
   } else if (warp >= 4) {
     // =============================== epilogue (both CTAs) =======================
-    const int ew = (warp - 4) & 3;  // TMEM lane quarter (must equal warp % 4)
+    const int ew = warp - 4;
     Stager st;
-    st.base = smem_u32(smem + Cfg::OFF_STG + (warp - 4) * STG_BYTES);
+    st.base = smem_u32(smem + Cfg::OFF_STG + ew * 2 * STG_BYTES);
     st.count = 0;
     st.lane = lane;
-    st.slot = (warp - 4) >> 2;
     uint32_t ti = 0;
     for (int tile = pair; tile < p.num_tiles; tile += num_pairs, ++ti) {
       const TileCoord t = decode_tile<2 * BM>(p, tile);
@@ -744,7 +741,7 @@ static int launch_gemm2(const GemmDev& dev, cudaStream_t stream) {
   }
   int pairs = num_sms() / 2;
   if (dev.num_tiles < pairs) pairs = dev.num_tiles;
-  kern<<<2 * pairs, 384, Cfg::SMEM_BYTES, stream>>>(dev);  // __cluster_dims__(2,1,1)
+  kern<<<2 * pairs, 256, Cfg::SMEM_BYTES, stream>>>(dev);  // __cluster_dims__(2,1,1)
   g_launches.fetch_add(1, std::memory_order_relaxed);
   NS2_CUDA_CHECK(cudaGetLastError());
   return kOk;
