@@ -14,7 +14,8 @@ fixed synthetic target) and the ranks all-reduce that 4-byte scalar over NCCL â€
 Printed JSON (one line, rank 0): the base contract keys plus
   roofline      dominant kernel = the FFN causal-conv GEMM (43% of the step's FLOPs): algorithmic FLOPs per launch
                 / mean launch time measured with CUDA events inside real steps, against MEASURED_PEAKS.json
-  cpu_baseline  the numpy oracle (a port of the reference's CPU path) on a bounded sample (batch 1), N=1 only
+  cpu_baseline  the torch-CPU port of the reference's path (oracle/denoiser_torch_port.py, all host threads) on a
+                bounded sample (batch 2 of the 32-sample step), N=1 only
   e2e           the same metric with HOST buffers: pinned-host -> device copy of the step's inputs and device ->
                 pinned-host copy of the full prediction inside the timed region (double-buffered on side streams)
 `--impl reference` times the reference-arm: the oracle port of the reference's CPU implementation on the host
@@ -262,35 +263,49 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+CPU_SAMPLE_BATCH = 2   # bounded sample of the 32-sample workload step
+
+
+class _TorchPort:
+    """oracle/denoiser_torch_port.py wrapped with the numpy oracle's calling convention."""
+
+    def __init__(self, mod):
+        self.mod = mod
+
+    def model_forward(self, P, cfg, x, t, dtype=None):
+        return self.mod.model_forward(P, cfg, x, t)
+
+
 def _oracle_setup(seed_model=None):
-    """numpy fp32 parameters of the cfg2 model for the oracle (reference CPU path port)."""
-    import numpy as np
+    """fp32 CPU parameters of the cfg2 model for the torch port of the reference CPU path (all host cores)."""
     import torch
     from naturalspeech2_pytorch_b200 import Model
-    from oracle import denoiser_oracle
+    from oracle import denoiser_oracle, denoiser_torch_port
+    torch.set_num_threads(os.cpu_count())
     if seed_model is None:
         torch.manual_seed(0)
         seed_model = Model(**CFG)
-    P = {k: v.detach().cpu().numpy().astype(np.float32) for k, v in seed_model.state_dict().items()}
+    P = {k: v.detach().cpu().float() for k, v in seed_model.state_dict().items()}
     cfg = denoiser_oracle.ModelConfig(**CFG)
-    rng = np.random.default_rng(0)
-    x = rng.standard_normal((1, SEQ, CFG["dim"]), dtype=np.float32)
-    t = rng.random((1,), dtype=np.float32)
-    return denoiser_oracle, P, cfg, x, t
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(CPU_SAMPLE_BATCH, SEQ, CFG["dim"], generator=g)
+    t = torch.rand(CPU_SAMPLE_BATCH, generator=g)
+    return _TorchPort(denoiser_torch_port), P, cfg, x, t
 
 
 def cpu_baseline(model=None, repeats=2):
-    """The oracle port of the reference's CPU path on a bounded sample: batch 1 of the workload (1/32 of a step)."""
-    import numpy as np
+    """The torch-CPU port of the reference's path on a bounded sample: batch 2 of the 32-sample workload step."""
     oracle, P, cfg, x, t = _oracle_setup(model)
-    oracle.model_forward(P, cfg, x, t, dtype=np.float32)  # warm-up (BLAS thread pool, page faults)
+    oracle.model_forward(P, cfg, x, t)  # warm-up (thread pool, page faults)
     best = float("inf")
     for _ in range(repeats):
         t0 = time.perf_counter()
-        oracle.model_forward(P, cfg, x, t, dtype=np.float32)
+        oracle.model_forward(P, cfg, x, t)
         best = min(best, time.perf_counter() - t0)
-    return {"value": round(1.0 / (best * BATCH), 5), "unit": "steps/s", "cores": os.cpu_count(), "kind": "port",
-            "sample": f"numpy fp32 oracle, batch 1 x seq 1024 ({best:.2f} s), scaled to the 32-sample step"}
+    return {"value": round(CPU_SAMPLE_BATCH / (best * BATCH), 5), "unit": "steps/s", "cores": os.cpu_count(),
+            "kind": "port",
+            "sample": f"torch fp32 CPU port of the reference path (oracle/denoiser_torch_port.py), batch "
+                      f"{CPU_SAMPLE_BATCH} x seq 1024 ({best:.2f} s), scaled x{BATCH // CPU_SAMPLE_BATCH} to the 32-sample step"}
 
 
 def run_reference(args):
@@ -298,19 +313,19 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import numpy as np
     oracle, P, cfg, x, t = _oracle_setup()
-    for _ in range(min(args.warmup, 1)):
-        oracle.model_forward(P, cfg, x, t, dtype=np.float32)
-    steps = min(args.steps, 5)  # each oracle "step" is a bounded sample (batch 1 = 1/32 of a workload step)
+    for _ in range(min(args.warmup, 2)):
+        oracle.model_forward(P, cfg, x, t)
+    steps = min(args.steps, 10)  # each timed call is a bounded sample (batch 2 = 1/16 of a workload step)
     t0 = time.perf_counter()
     for _ in range(steps):
-        oracle.model_forward(P, cfg, x, t, dtype=np.float32)
+        oracle.model_forward(P, cfg, x, t)
     dt = (time.perf_counter() - t0) / steps
-    value = 1.0 / (dt * BATCH)
-    sample = f"numpy fp32 oracle port of the reference CPU path, batch 1 x seq 1024 per timed call ({dt:.2f} s), scaled x32 to the workload step"
+    value = CPU_SAMPLE_BATCH / (dt * BATCH)
+    sample = (f"torch fp32 CPU port of the reference path (oracle/denoiser_torch_port.py, all host threads), batch "
+              f"{CPU_SAMPLE_BATCH} x seq 1024 per timed call ({dt:.2f} s), scaled x{BATCH // CPU_SAMPLE_BATCH} to the workload step")
     line = {"impl": "reference", "metric": "denoiser-steps/sec", "value": round(value, 5), "unit": "steps/s",
-            "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": round(dt * BATCH * 1e3, 1),
+            "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 2), "ms_per_step": round(dt * BATCH / CPU_SAMPLE_BATCH * 1e3, 1),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "global_batch": BATCH, "seq_len": SEQ, "parallelism": "cpu"},
             "cpu_baseline": {"value": round(value, 5), "unit": "steps/s", "cores": os.cpu_count(), "kind": "port",
@@ -322,7 +337,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")

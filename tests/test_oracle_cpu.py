@@ -112,3 +112,18 @@ def test_rvq_oracle_matches_encodec_port():
     np.testing.assert_array_equal(dec, z["decoded_random"])
     # duplicate codeword: the oracle must return the lower index
     assert (rvq_oracle.encode(cbn[0, 7][None], cbn)[0, 0]) == 3
+
+
+@pytest.mark.parametrize("name", ["uncond_small", "cond_small", "cond_samedim"])
+def test_torch_port_matches_reference(name):
+    """The torch-CPU port used for bench.py's reference arm reproduces the reference fp32/fp64 outputs."""
+    from oracle import denoiser_torch_port as tp
+    z, kwargs, seed = load_model_golden(name)
+    model = build_model(kwargs, seed)
+    P = {k: v.detach().double() for k, v in model.state_dict().items()}
+    cfg = oracle_config(kwargs)
+    extra = {}
+    if kwargs.get("condition_on_prompt"):
+        extra = dict(prompt=torch.from_numpy(z["in_prompt"]).double(), cond=torch.from_numpy(z["in_cond"]).double())
+    out = tp.model_forward(P, cfg, torch.from_numpy(z["in_x"]).double(), torch.from_numpy(z["in_times"]).double(), **extra)
+    assert err_stats(out.numpy(), z["out_fp64"])[0] < 1e-9
