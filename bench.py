@@ -113,7 +113,8 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=300))
 
     torch.manual_seed(0)
     model = Model(**CFG).to(dev).eval()
@@ -138,7 +139,7 @@ def run_ours(args):
 
     def barrier():
         if world > 1:
-            dist.barrier()
+            dist.barrier(device_ids=[local_rank])
         torch.cuda.synchronize()
 
     for _ in range(max(args.warmup, 3)):
@@ -222,7 +223,7 @@ def run_ours(args):
     if rank == 0:
         model._prof = []
         for _ in range(3):
-            step()
+            model(x, times)  # rank-local: no collective here (the other ranks have left the step loop)
         torch.cuda.synchronize()
         conv_ms = [a.elapsed_time(b) for (name, a, b) in model._prof if name == "ff_conv"]
         by_name = {}
