@@ -52,6 +52,17 @@ def _peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback (B200_PROFILING.md)"
 
 
+def _ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
+    `ncu --set full` capture (profiles/r01_dominant_kernel_ncu.json); None if the capture is absent."""
+    p = ROOT / "profiles" / "r01_dominant_kernel_ncu.json"
+    if not p.exists():
+        return None
+    d = json.loads(p.read_text())
+    vals = [(l["dram_read_MB"] + l["dram_write_MB"]) * 1e6 for l in d["launches"]]
+    return round(sum(vals) / len(vals))
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -120,6 +131,7 @@ def run_ours(args):
     model = Model(**CFG).to(dev).eval()
     model.packed()
     model.freeze_packed = True
+    model.use_cuda_graphs = not args.no_cuda_graphs   # the step replays one captured graph (111 kernel nodes)
     g = torch.Generator(device="cpu").manual_seed(1 + rank)
     x_host = torch.randn(BATCH, SEQ, CFG["dim"], generator=g).pin_memory()
     t_host = torch.rand(BATCH, generator=g).pin_memory()
@@ -145,10 +157,13 @@ def run_ours(args):
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
+    graphs = model.use_cuda_graphs
+    model.use_cuda_graphs = False     # count this library's launches of one step with eager launches
     l0 = ops.launch_count()
     step()
     torch.cuda.synchronize()
     launches_per_step = ops.launch_count() - l0
+    model.use_cuda_graphs = graphs
 
     # ------------------------------- timed region: K steps, device-resident inputs -------------------
     sampler = ClockSampler(local_rank)
@@ -238,7 +253,7 @@ def run_ours(args):
                 "achieved": round(achieved, 1), "peak": peak, "unit": "TFLOP/s", "frac": round(achieved / peak, 4),
                 "peak_source": peak_src + ", sustained bf16 (kernel timed inside a long step)",
                 "flops_per_launch": CONV_FLOPS_PER_LAUNCH, "ms_per_launch": round(conv_mean, 4),
-                "traffic": None,
+                "traffic": _ncu_traffic(),
                 "step_tflops": round(FLOPS_PER_SAMPLE * BATCH / (ms_per_step * 1e-3) / 1e12, 1),
                 "step_frac_of_peak": round(FLOPS_PER_SAMPLE * BATCH / (ms_per_step * 1e-3) / 1e12 / peak, 4),
                 "per_op_ms_per_step": {k: round(sum(v) / 3, 4) for k, v in sorted(by_name.items())}}
@@ -342,6 +357,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cuda-graphs", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

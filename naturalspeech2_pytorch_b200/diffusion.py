@@ -57,7 +57,7 @@ class NaturalSpeech2(nn.Module):
                  use_ddim=True, noise_schedule="sigmoid", objective="v", schedule_kwargs: dict = dict(),
                  time_difference=0., min_snr_loss_weight=True, min_snr_gamma=5, train_prob_self_cond=0.9,
                  rvq_cross_entropy_loss_weight=0., scale=1.,
-                 conditioner: Optional[Callable] = None, **conditioning_kwargs):
+                 conditioner: Optional[Callable] = None, cuda_graphs: bool = True, **conditioning_kwargs):
         super().__init__()
         if not isinstance(model, Model):
             raise TypeError("model must be a naturalspeech2_pytorch_b200.Model")
@@ -93,6 +93,7 @@ class NaturalSpeech2(nn.Module):
         if rvq_cross_entropy_loss_weight != 0:
             raise NotImplementedError("codec.rq cross-entropy head (SURVEY a17) is optional and not built")
         self.conditioner = conditioner
+        self.cuda_graphs = cuda_graphs  # sampling loop: replay one captured CUDA graph per denoiser step
         self.conditioning_kwargs = conditioning_kwargs  # accepted for signature parity (encoder hyper-parameters)
 
     @property
@@ -121,6 +122,8 @@ class NaturalSpeech2(nn.Module):
             assert _exists(prompt) and _exists(cond)
             # timestep-invariant work (perceiver, prompt FiLM vector, aligned-condition projection) once
             conditioning = self.model.precompute_conditioning(prompt, cond, shape[1])
+        graphs_before = self.model.use_cuda_graphs
+        self.model.use_cuda_graphs = graphs_before or self.cuda_graphs
         for times, times_next in time_pairs:
             gamma = self.gamma_schedule(times)
             gamma_next = self.gamma_schedule(times_next)
@@ -134,6 +137,7 @@ class NaturalSpeech2(nn.Module):
                 v = self.model.forward_with_cond_scale(audio, times, cond_scale=cond_scale)
             ops.ddim_step(audio, v, alpha.contiguous(), sigma.contiguous(), alpha_next.contiguous(),
                           sigma_next.contiguous())
+        self.model.use_cuda_graphs = graphs_before
         return audio
 
     def process_prompt(self, prompt=None):

@@ -89,8 +89,11 @@ def denoiser_cfg(name, kwargs, B, N, flops_per_sample, cond=False, reps=20):
     t = torch.rand(B, device="cuda")
     if not cond:
         ms = time_ms(lambda: model(x, t), reps)
-        emit({"bench": name, "batch": B, "seq": N, "ms_per_step": round(ms, 4), "steps_per_s": round(1e3 / ms, 2),
-              "tflops": round(flops_per_sample * B / ms / 1e9, 1)})
+        model.use_cuda_graphs = True
+        ms_g = time_ms(lambda: model(x, t), reps)
+        emit({"bench": name, "batch": B, "seq": N, "ms_per_step_eager": round(ms, 4),
+              "ms_per_step_cuda_graph": round(ms_g, 4), "steps_per_s": round(1e3 / ms_g, 2),
+              "tflops": round(flops_per_sample * B / ms_g / 1e9, 1)})
         return
     prompt = torch.randn(B, 103, kwargs["dim_prompt"], device="cuda")
     cnd = torch.randn(B, kwargs["dim_prompt"], N, device="cuda")
