@@ -19,3 +19,8 @@ torch.cuda.synchronize(); log("first replay synced; equal:", torch.equal(e, g))
 for i in range(5):
     g = m(x, t)
 torch.cuda.synchronize(); log("5 replays synced; equal:", torch.equal(e, g))
+if "ddim" in sys.argv:
+    from naturalspeech2_pytorch_b200 import NaturalSpeech2
+    ns = NaturalSpeech2(m, target_sample_hz=24000, timesteps=4)
+    out = ns.sample(length=256, batch_size=2); torch.cuda.synchronize(); log("ddim sample ok", tuple(out.shape))
+    out = ns.sample(length=256, batch_size=2); torch.cuda.synchronize(); log("ddim sample 2 ok")
