@@ -36,7 +36,7 @@ constexpr int OFF_BAR = OFF_P + P_BYTES;
 constexpr int SMEM_BYTES = OFF_BAR + 256;              // 112.25 KB -> two CTAs per SM
 constexpr int TMEM_COLS = 256;                         // two CTAs per SM share the 512 columns
 constexpr int TM_S = 0;     // S at columns [0, 128)
-constexpr int TM_O = 128;   // O_j buffers at columns 128 and 192
+constexpr int TM_O = 128;   // O accumulator at columns [128, 192)
 }  // namespace attn
 
 struct AttnDev {
@@ -53,6 +53,11 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
+// Two-pass flash attention.  Pass A computes only the exact row maxima (S = Q.K^T, running max, nothing else);
+// pass B recomputes S tile by tile, forms P = exp2(S*c - m) against the FINAL maximum and lets the tensor core
+// accumulate O += P.V in TMEM across all key tiles.  No running rescale, no per-tile read-back of partial outputs,
+// one exp pass: ~600 issue slots per 128x128 tile per warp instead of ~1050, at the price of issuing Q.K^T twice
+// (tensor time stays below the MUFU time of the exponentials).
 // Two CTAs are resident per SM (112 KB smem, 256 TMEM columns, <=170 registers each): while one CTA's softmax
 // warps occupy the MUFU/FMA pipes, the other CTA's MMAs occupy the tensor core.
 __global__ void __launch_bounds__(192, 2) attn_fwd_kernel(const __grid_constant__ AttnDev p) {
@@ -62,9 +67,9 @@ __global__ void __launch_bounds__(192, 2) attn_fwd_kernel(const __grid_constant_
   uint64_t* q_full = bars + 0;
   uint64_t* kv_full = bars + 1;   // [2]
   uint64_t* kv_empty = bars + 3;  // [2]
-  uint64_t* s_full = bars + 5;
-  uint64_t* p_full = bars + 6;
-  uint64_t* o_full = bars + 7;    // [2]
+  uint64_t* s_full = bars + 5;    // MMA -> softmax: S tile ready
+  uint64_t* s_done = bars + 6;    // softmax -> MMA: S tile consumed (and, in pass B, P tile written); 128 arrivals
+  uint64_t* pv_done = bars + 7;   // MMA -> softmax: P.V retired (P buffer reusable; after the last tile: O complete)
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 9);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -72,6 +77,7 @@ __global__ void __launch_bounds__(192, 2) attn_fwd_kernel(const __grid_constant_
   const int head = blockIdx.y;
   const int b = blockIdx.z;
   const int T = (p.kv_len + BKV - 1) / BKV;
+  // global tile counter g: pass A = [0, T), pass B = [T, 2T); key tile j = g mod T
 
   if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) {
     printf("ns2 attn: dynamic shared memory is not 1024-byte aligned\n");
@@ -85,11 +91,11 @@ __global__ void __launch_bounds__(192, 2) attn_fwd_kernel(const __grid_constant_
   if (warp == 5 && lane == 0) {
     mbar_init(smem_u32(q_full), 1);
     mbar_init(smem_u32(s_full), 1);
-    mbar_init(smem_u32(p_full), 128);
+    mbar_init(smem_u32(s_done), 128);
+    mbar_init(smem_u32(pv_done), 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(smem_u32(&kv_full[i]), 1);
       mbar_init(smem_u32(&kv_empty[i]), 1);
-      mbar_init(smem_u32(&o_full[i]), 1);
     }
     fence_barrier_init();
   }
@@ -104,14 +110,16 @@ __global__ void __launch_bounds__(192, 2) attn_fwd_kernel(const __grid_constant_
     if (lane == 0) {
       mbar_arrive_expect_tx(smem_u32(q_full), Q_BYTES);
       tma_load_3d(smem_u32(smem + OFF_Q), &p.tmQ, smem_u32(q_full), head * DH, q0, b);
-      for (int j = 0; j < T; ++j) {
-        const int st = j & 1;
-        const uint32_t ph = (j >> 1) & 1;
+      for (int g = 0; g < 2 * T; ++g) {
+        const int st = g & 1;
+        const uint32_t ph = (g >> 1) & 1;
+        const bool pass_b = g >= T;
+        const int j = pass_b ? g - T : g;
         mbar_wait(smem_u32(&kv_empty[st]), ph ^ 1);
         const uint32_t fb = smem_u32(&kv_full[st]);
-        mbar_arrive_expect_tx(fb, 2 * KV_BYTES);
+        mbar_arrive_expect_tx(fb, pass_b ? 2 * KV_BYTES : KV_BYTES);
         tma_load_3d(smem_u32(smem + OFF_K + st * KV_BYTES), &p.tmK, fb, head * DH, j * BKV, b);
-        tma_load_3d(smem_u32(smem + OFF_V + st * KV_BYTES), &p.tmV, fb, head * DH, j * BKV, b);
+        if (pass_b) tma_load_3d(smem_u32(smem + OFF_V + st * KV_BYTES), &p.tmV, fb, head * DH, j * BKV, b);
       }
     }
   } else if (warp == 5) {
@@ -121,35 +129,38 @@ __global__ void __launch_bounds__(192, 2) attn_fwd_kernel(const __grid_constant_
       constexpr uint32_t idesc_o = umma_idesc_f16(BQ, DH, 1, 0, /*V is MN-major*/ 1);
       const uint64_t dq = umma_desc_sw128(smem_u32(smem + OFF_Q), 16, 1024);
       const uint32_t pbase = smem_u32(smem + OFF_P);
-      auto issue_s = [&](int j) {
-        const int st = j & 1;
-        mbar_wait(smem_u32(&kv_full[st]), (j >> 1) & 1);
+      auto issue_s = [&](int g) {
+        const int st = g & 1;
+        mbar_wait(smem_u32(&kv_full[st]), (g >> 1) & 1);
         tc_fence_after();
         const uint64_t dk = umma_desc_sw128(smem_u32(smem + OFF_K + st * KV_BYTES), 16, 1024);
 #pragma unroll
         for (int k = 0; k < DH / 16; ++k)
           tc_mma_f16(tmem_base + TM_S, dq + 2 * k, dk + 2 * k, idesc_s, k > 0);
         tc_commit(smem_u32(s_full));
+        if (g < T) tc_commit(smem_u32(&kv_empty[st]));  // pass A: the K tile is free once S is computed
       };
       mbar_wait(smem_u32(q_full), 0);
       issue_s(0);
-      for (int j = 0; j < T; ++j) {
-        const int st = j & 1;
-        // P_j is in smem and the softmax warps are done reading S_j
-        mbar_wait(smem_u32(p_full), j & 1);
+      for (int g = 0; g < 2 * T; ++g) {
+        // the softmax warps are done with S_g (pass B: and P_g is in shared memory)
+        mbar_wait(smem_u32(s_done), g & 1);
         tc_fence_after();
-        if (j + 1 < T) issue_s(j + 1);  // runs ahead of P_j.V_j so the next softmax can start early
-        const uint32_t vbase = smem_u32(smem + OFF_V + st * KV_BYTES);
+        if (g + 1 < 2 * T) issue_s(g + 1);  // next S runs ahead of this tile's P.V
+        if (g >= T) {
+          const int st = g & 1;
+          const uint32_t vbase = smem_u32(smem + OFF_V + st * KV_BYTES);
 #pragma unroll
-        for (int k = 0; k < BKV / 16; ++k) {
-          // A = P: K-major, 64-key atoms of 16 KB, 32 bytes per 16-key step inside an atom
-          const uint64_t dp = umma_desc_sw128(pbase + (k >> 2) * (BQ * 128) + (k & 3) * 32, 16, 1024);
-          // B = V: MN-major (64 dh contiguous per key row of 128 B); 16 keys = 2048 bytes per step
-          const uint64_t dv = umma_desc_sw128(vbase + k * 2048, 1024, 1024);
-          tc_mma_f16(tmem_base + TM_O + st * DH, dp, dv, idesc_o, k > 0);
+          for (int k = 0; k < BKV / 16; ++k) {
+            // A = P: K-major, 64-key atoms of 16 KB, 32 bytes per 16-key step inside an atom
+            const uint64_t dp = umma_desc_sw128(pbase + (k >> 2) * (BQ * 128) + (k & 3) * 32, 16, 1024);
+            // B = V: MN-major (64 dh contiguous per key row of 128 B); 16 keys = 2048 bytes per step
+            const uint64_t dv = umma_desc_sw128(vbase + k * 2048, 1024, 1024);
+            tc_mma_f16(tmem_base + TM_O, dp, dv, idesc_o, (g > T) | (k > 0));  // O accumulates over all key tiles
+          }
+          tc_commit(smem_u32(pv_done));
+          tc_commit(smem_u32(&kv_empty[st]));
         }
-        tc_commit(smem_u32(&o_full[st]));
-        tc_commit(smem_u32(&kv_empty[st]));
       }
     }
   } else {
@@ -157,135 +168,120 @@ __global__ void __launch_bounds__(192, 2) attn_fwd_kernel(const __grid_constant_
     const int row = warp * 32 + lane;
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
     const float c = p.scale_log2e;
-    float o_acc[DH];
-#pragma unroll
-    for (int i = 0; i < DH; ++i) o_acc[i] = 0.f;
-    float m_run = -INFINITY, l_run = 0.f, a_prev = 0.f;
     uint8_t* prow = smem + OFF_P + row * 128;
 
-    auto accumulate_o = [&](int jprev, float a) {  // o_full[jprev & 1] has already been waited on
-      const int st = jprev & 1;
-      uint32_t r0[32], r1[32];
-      tmem_ld32(lane_addr + TM_O + st * DH, r0);
-      tmem_ld32(lane_addr + TM_O + st * DH + 32, r1);
-      tmem_ld_wait();
-#pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        o_acc[i] = fmaf(o_acc[i], a, __uint_as_float(r0[i]));
-        o_acc[32 + i] = fmaf(o_acc[32 + i], a, __uint_as_float(r1[i]));
-      }
-    };
-
-    for (int j = 0; j < T; ++j) {
-      mbar_wait(smem_u32(s_full), j & 1);
+    // ---- pass A: exact row maximum over all keys ----
+    float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+    for (int g = 0; g < T; ++g) {
+      mbar_wait(smem_u32(s_full), g & 1);
       tc_fence_after();
-      const int valid = p.kv_len - j * BKV;  // columns >= valid are padding keys
+      const int valid = p.kv_len - g * BKV;  // columns >= valid are padding keys
+#pragma unroll 1
+      for (int cc = 0; cc < BKV / 64; ++cc) {
+        uint32_t r0[32], r1[32];
+        tmem_ld32(lane_addr + TM_S + cc * 64, r0);
+        tmem_ld32(lane_addr + TM_S + cc * 64 + 32, r1);
+        tmem_ld_wait();
+        if (valid >= BKV) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            m0 = fmaxf(m0, __uint_as_float(r0[i]));
+            m1 = fmaxf(m1, __uint_as_float(r0[i + 1]));
+            m2 = fmaxf(m2, __uint_as_float(r1[i]));
+            m3 = fmaxf(m3, __uint_as_float(r1[i + 1]));
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            if (cc * 64 + i < valid) m0 = fmaxf(m0, __uint_as_float(r0[i]));
+            if (cc * 64 + 32 + i < valid) m1 = fmaxf(m1, __uint_as_float(r1[i]));
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(smem_u32(s_done));
+    }
+    const float mc = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) * c;  // scaled maximum (log2 domain)
+
+    // ---- pass B: probabilities against the final maximum; P.V accumulates in TMEM ----
+    float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+    for (int g = T; g < 2 * T; ++g) {
+      const int j = g - T;
+      mbar_wait(smem_u32(s_full), g & 1);
+      tc_fence_after();
+      if (j > 0) mbar_wait(smem_u32(pv_done), (j - 1) & 1);  // previous P.V retired: the P buffer is free
+      const int valid = p.kv_len - j * BKV;
       const bool full = valid >= BKV;
-      // pass 1: row maximum of the raw scores (64 columns per TMEM round trip, 4 independent max chains)
-      float m_tile;
-      {
-        float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
 #pragma unroll 1
-        for (int cc = 0; cc < BKV / 64; ++cc) {
-          uint32_t r0[32], r1[32];
-          tmem_ld32(lane_addr + TM_S + cc * 64, r0);
-          tmem_ld32(lane_addr + TM_S + cc * 64 + 32, r1);
-          tmem_ld_wait();
-          if (full) {
+      for (int cc = 0; cc < BKV / 32; ++cc) {
+        uint32_t r[32];
+        tmem_ld32(lane_addr + TM_S + cc * 32, r);
+        tmem_ld_wait();
+        uint32_t pk[16];
+        if (full) {
 #pragma unroll
-            for (int i = 0; i < 32; i += 2) {
-              m0 = fmaxf(m0, __uint_as_float(r0[i]));
-              m1 = fmaxf(m1, __uint_as_float(r0[i + 1]));
-              m2 = fmaxf(m2, __uint_as_float(r1[i]));
-              m3 = fmaxf(m3, __uint_as_float(r1[i + 1]));
-            }
-          } else {
+          for (int i = 0; i < 16; i += 2) {
+            const float p0 = ex2_approx(fmaf(__uint_as_float(r[2 * i]), c, -mc));
+            const float p1 = ex2_approx(fmaf(__uint_as_float(r[2 * i + 1]), c, -mc));
+            const float p2 = ex2_approx(fmaf(__uint_as_float(r[2 * i + 2]), c, -mc));
+            const float p3 = ex2_approx(fmaf(__uint_as_float(r[2 * i + 3]), c, -mc));
+            l0 += p0; l1 += p1; l2 += p2; l3 += p3;
+            pk[i] = pack_bf16x2(p0, p1);
+            pk[i + 1] = pack_bf16x2(p2, p3);
+          }
+        } else {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              if (cc * 64 + i < valid) m0 = fmaxf(m0, __uint_as_float(r0[i]));
-              if (cc * 64 + 32 + i < valid) m1 = fmaxf(m1, __uint_as_float(r1[i]));
-            }
+          for (int i = 0; i < 16; ++i) {
+            const int c0 = cc * 32 + 2 * i;
+            const float p0 = (c0 < valid) ? ex2_approx(fmaf(__uint_as_float(r[2 * i]), c, -mc)) : 0.f;
+            const float p1 = (c0 + 1 < valid) ? ex2_approx(fmaf(__uint_as_float(r[2 * i + 1]), c, -mc)) : 0.f;
+            l0 += p0; l1 += p1;
+            pk[i] = pack_bf16x2(p0, p1);
           }
         }
-        m_tile = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
-      }
-      const float m_new = fmaxf(m_run, m_tile * c);
-      const float a = ex2_approx(m_run - m_new);  // 0 on the first tile (m_run = -inf)
-      if (j > 0) {
-        // P.V of the previous tile has retired: the P buffer is free and O_{j-1} can be read
-        mbar_wait(smem_u32(&o_full[(j - 1) & 1]), ((j - 1) >> 1) & 1);
-        tc_fence_after();
-      }
-      // pass 2: probabilities -> bf16 -> swizzled smem; row sum in fp32 (4 independent chains)
-      float l_tile;
-      {
-        float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
-#pragma unroll 1
-        for (int cc = 0; cc < BKV / 32; ++cc) {
-          uint32_t r[32];
-          tmem_ld32(lane_addr + TM_S + cc * 32, r);
-          tmem_ld_wait();
-          uint32_t pk[16];
-          if (full) {
+        // 32 columns = 4 chunks of 16 bytes; chunk index within the 64-key atom is XOR-swizzled with row&7
+        uint8_t* atom = prow + (cc >> 1) * (BQ * 128);
 #pragma unroll
-            for (int i = 0; i < 16; i += 2) {
-              const float p0 = ex2_approx(fmaf(__uint_as_float(r[2 * i]), c, -m_new));
-              const float p1 = ex2_approx(fmaf(__uint_as_float(r[2 * i + 1]), c, -m_new));
-              const float p2 = ex2_approx(fmaf(__uint_as_float(r[2 * i + 2]), c, -m_new));
-              const float p3 = ex2_approx(fmaf(__uint_as_float(r[2 * i + 3]), c, -m_new));
-              l0 += p0; l1 += p1; l2 += p2; l3 += p3;
-              pk[i] = pack_bf16x2(p0, p1);
-              pk[i + 1] = pack_bf16x2(p2, p3);
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const int c0 = cc * 32 + 2 * i;
-              const float p0 = (c0 < valid) ? ex2_approx(fmaf(__uint_as_float(r[2 * i]), c, -m_new)) : 0.f;
-              const float p1 =
-                  (c0 + 1 < valid) ? ex2_approx(fmaf(__uint_as_float(r[2 * i + 1]), c, -m_new)) : 0.f;
-              l0 += p0; l1 += p1;
-              pk[i] = pack_bf16x2(p0, p1);
-            }
-          }
-          // 32 columns = 4 chunks of 16 bytes; chunk index within the 64-key atom is XOR-swizzled with row&7
-          uint8_t* atom = prow + (cc >> 1) * (BQ * 128);
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const int chunk = (cc & 1) * 4 + q;
-            *reinterpret_cast<uint4*>(atom + ((chunk ^ (row & 7)) << 4)) =
-                make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
-          }
+        for (int q = 0; q < 4; ++q) {
+          const int chunk = (cc & 1) * 4 + q;
+          *reinterpret_cast<uint4*>(atom + ((chunk ^ (row & 7)) << 4)) =
+              make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
         }
-        l_tile = (l0 + l1) + (l2 + l3);
       }
-      l_run = fmaf(l_run, a, l_tile);
-      m_run = m_new;
-      // publish P_j: generic-proxy writes -> async proxy, TMEM reads of S_j ordered before the next MMA
+      // publish P_j: generic-proxy writes -> async proxy, TMEM reads of S ordered before the next MMA
       fence_proxy_async_smem();
       tc_fence_before();
-      mbar_arrive(smem_u32(p_full));
-      // fold in the previous tile's P.V while the tensor core works on this one
-      if (j > 0) accumulate_o(j - 1, a_prev);
-      a_prev = a;
+      mbar_arrive(smem_u32(s_done));
     }
-    mbar_wait(smem_u32(&o_full[(T - 1) & 1]), ((T - 1) >> 1) & 1);
+    // ---- epilogue: O / l ----
+    mbar_wait(smem_u32(pv_done), (T - 1) & 1);
     tc_fence_after();
-    accumulate_o(T - 1, a_prev);
-
+    const float inv = 1.0f / ((l0 + l1) + (l2 + l3));
+    uint32_t o0[32], o1[32];
+    tmem_ld32(lane_addr + TM_O, o0);
+    tmem_ld32(lane_addr + TM_O + 32, o1);
+    tmem_ld_wait();
     if (q0 + row < p.q_len) {
-      const float inv = 1.0f / l_run;
       __nv_bfloat16* op = p.out + static_cast<long long>(b) * p.o_bs +
                           static_cast<long long>(q0 + row) * p.o_rs + head * DH;
       uint4* o4 = reinterpret_cast<uint4*>(op);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
+      for (int i = 0; i < 4; ++i) {
         uint4 w;
-        w.x = pack_bf16x2(o_acc[8 * i + 0] * inv, o_acc[8 * i + 1] * inv);
-        w.y = pack_bf16x2(o_acc[8 * i + 2] * inv, o_acc[8 * i + 3] * inv);
-        w.z = pack_bf16x2(o_acc[8 * i + 4] * inv, o_acc[8 * i + 5] * inv);
-        w.w = pack_bf16x2(o_acc[8 * i + 6] * inv, o_acc[8 * i + 7] * inv);
+        w.x = pack_bf16x2(__uint_as_float(o0[8 * i + 0]) * inv, __uint_as_float(o0[8 * i + 1]) * inv);
+        w.y = pack_bf16x2(__uint_as_float(o0[8 * i + 2]) * inv, __uint_as_float(o0[8 * i + 3]) * inv);
+        w.z = pack_bf16x2(__uint_as_float(o0[8 * i + 4]) * inv, __uint_as_float(o0[8 * i + 5]) * inv);
+        w.w = pack_bf16x2(__uint_as_float(o0[8 * i + 6]) * inv, __uint_as_float(o0[8 * i + 7]) * inv);
         o4[i] = w;
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        uint4 w;
+        w.x = pack_bf16x2(__uint_as_float(o1[8 * i + 0]) * inv, __uint_as_float(o1[8 * i + 1]) * inv);
+        w.y = pack_bf16x2(__uint_as_float(o1[8 * i + 2]) * inv, __uint_as_float(o1[8 * i + 3]) * inv);
+        w.z = pack_bf16x2(__uint_as_float(o1[8 * i + 4]) * inv, __uint_as_float(o1[8 * i + 5]) * inv);
+        w.w = pack_bf16x2(__uint_as_float(o1[8 * i + 6]) * inv, __uint_as_float(o1[8 * i + 7]) * inv);
+        o4[4 + i] = w;
       }
     }
   }
