@@ -191,13 +191,14 @@ __global__ void __launch_bounds__(192, 2) attn_fwd_kernel(const __grid_constant_
       const int valid = p.kv_len - j * BKV;  // columns >= valid are padding keys
       const bool full = valid >= BKV;
       const uint32_t s_addr = lane_addr + TM_S + bsel * BKV;
-      // pass 1: row maximum of the raw scores (4 independent chains)
+      // S_j is read from TMEM exactly once (TMEM reads run at ~64 B/clk per SM and were the bottleneck of the
+      // two-pass version): 64 scores stay in registers for both the maximum and the exponentials
+      uint32_t r0[32], r1[32];
+      tmem_ld32(s_addr, r0);
+      tmem_ld32(s_addr + 32, r1);
+      tmem_ld_wait();
       float m_tile;
       {
-        uint32_t r0[32], r1[32];
-        tmem_ld32(s_addr, r0);
-        tmem_ld32(s_addr + 32, r1);
-        tmem_ld_wait();
         float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
         if (full) {
 #pragma unroll
@@ -218,17 +219,13 @@ __global__ void __launch_bounds__(192, 2) attn_fwd_kernel(const __grid_constant_
       }
       const float m_new = fmaxf(m_run, m_tile * c);
       const float a = ex2_approx(m_run - m_new);  // 0 on the first tile (m_run = -inf)
-      // pass 2: probabilities -> bf16 -> swizzled smem; row sum in fp32 (4 independent chains)
+      // probabilities -> bf16 -> swizzled smem; row sum in fp32 (4 independent chains)
       // (P buffer `bsel` was last read by P.V of tile j-2, whose completion was awaited in iteration j-1)
       float l_tile;
       {
         uint8_t* prow = smem + OFF_P + bsel * P_BYTES + row * 128;
         float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
-#pragma unroll 1
-        for (int cc = 0; cc < BKV / 32; ++cc) {
-          uint32_t r[32];
-          tmem_ld32(s_addr + cc * 32, r);
-          tmem_ld_wait();
+        auto chunk32 = [&](const uint32_t (&r)[32], int cc) {
           uint32_t pk[16];
           if (full) {
 #pragma unroll
@@ -259,7 +256,9 @@ __global__ void __launch_bounds__(192, 2) attn_fwd_kernel(const __grid_constant_
             *reinterpret_cast<uint4*>(prow + ((chunk ^ (row & 7)) << 4)) =
                 make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
           }
-        }
+        };
+        chunk32(r0, 0);
+        chunk32(r1, 1);
         l_tile = (l0 + l1) + (l2 + l3);
       }
       l_run = fmaf(l_run, a, l_tile);
