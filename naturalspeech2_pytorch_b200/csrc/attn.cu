@@ -48,6 +48,12 @@ struct AttnDev {
   float scale_log2e;
 };
 
+// bf16 pair from two non-negative finite floats with round-half-up done on the integer pipe (IADD + PRMT): the
+// F2FP conversion shares the 16-lane XU pipe with ex2, which bounds the softmax throughput.
+__device__ __forceinline__ uint32_t pack_bf16x2_pos(float lo, float hi) {
+  return __byte_perm(__float_as_uint(lo) + 0x8000u, __float_as_uint(hi) + 0x8000u, 0x7632);
+}
+
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -235,8 +241,8 @@ __global__ void __launch_bounds__(192, 2) attn_fwd_kernel(const __grid_constant_
               const float p2 = ex2_approx(fmaf(__uint_as_float(r[2 * i + 2]), c, -m_new));
               const float p3 = ex2_approx(fmaf(__uint_as_float(r[2 * i + 3]), c, -m_new));
               l0 += p0; l1 += p1; l2 += p2; l3 += p3;
-              pk[i] = pack_bf16x2(p0, p1);
-              pk[i + 1] = pack_bf16x2(p2, p3);
+              pk[i] = pack_bf16x2_pos(p0, p1);
+              pk[i + 1] = pack_bf16x2_pos(p2, p3);
             }
           } else {
 #pragma unroll
@@ -246,7 +252,7 @@ __global__ void __launch_bounds__(192, 2) attn_fwd_kernel(const __grid_constant_
               const float p1 =
                   (c0 + 1 < valid) ? ex2_approx(fmaf(__uint_as_float(r[2 * i + 1]), c, -m_new)) : 0.f;
               l0 += p0; l1 += p1;
-              pk[i] = pack_bf16x2(p0, p1);
+              pk[i] = pack_bf16x2_pos(p0, p1);
             }
           }
           // 32 columns = 4 chunks of 16 bytes of the 128-byte row; chunk index XOR-swizzled with row&7
