@@ -484,7 +484,8 @@ class Model(nn.Module):
                 self._forward_impl(xs, ts, None, None, None, p_eff, conditioning)
             torch.cuda.current_stream().wait_stream(side)
             graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
+            # thread_local: other threads (e.g. the NCCL watchdog) may touch CUDA while this thread captures
+            with torch.cuda.graph(graph, capture_error_mode="thread_local"):
                 out = self._forward_impl(xs, ts, None, None, None, p_eff, conditioning)
             entry = (graph, xs, ts, out, conditioning)  # keeps the conditioning tensors alive
             self._graphs[key] = entry
