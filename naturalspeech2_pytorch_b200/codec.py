@@ -48,6 +48,9 @@ class EncodecRVQ(nn.Module):
     def quantize(self, frames: torch.Tensor, stats: Optional[torch.Tensor] = None):
         """frames (..., 128) fp32 -> (codes (..., Q) int64, emb (..., 128) fp32 = sum of the chosen codewords)."""
         shp = frames.shape[:-1]
+        if frames.numel() == 0:  # empty batch: nothing to launch (the reference returns empty tensors too)
+            return (torch.empty(*shp, self.num_quantizers, dtype=torch.int64, device=frames.device),
+                    torch.empty(*shp, 128, dtype=torch.float32, device=frames.device))
         flat = frames.reshape(-1, 128).float().contiguous()
         codes = ops.rvq_encode(flat, self.codebooks, self._prep(), stats=stats)
         emb = ops.rvq_decode(codes, self.codebooks)

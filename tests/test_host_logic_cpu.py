@@ -128,3 +128,12 @@ def test_scalar_loss_allreduce_gloo_world2():
         assert p.exitcode == 0
     expect = float((torch.arange(7, dtype=torch.float32) ** 2).mean())
     assert res[0] == pytest.approx(expect) and res[1] == pytest.approx(expect)
+
+
+def test_rvq_empty_input_returns_empty_tensors():
+    from naturalspeech2_pytorch_b200 import EncodecRVQ
+    codec = EncodecRVQ(torch.randn(8, 1024, 128))
+    codes, emb = codec.quantize(torch.empty(0, 128))
+    assert codes.shape == (0, 8) and codes.dtype == torch.int64 and emb.shape == (0, 128)
+    codes, emb = codec.quantize(torch.empty(2, 0, 128))
+    assert codes.shape == (2, 0, 8) and emb.shape == (2, 0, 128)
