@@ -545,13 +545,16 @@ struct Gemm2Cfg {
   static constexpr int STG_TOTAL = 4 * 2 * STG_BYTES;    // 4 epilogue warps x 2 staging boxes
   static constexpr int STAGES = (192 * 1024) / STAGE_BYTES > 8 ? 8 : (192 * 1024) / STAGE_BYTES;
   static constexpr int ACC_COLS = BN * NACC;
-  static constexpr int ACC_STRIDE = (ACC_COLS <= 128) ? 128 : 256;  // column offset of the second stage
-  static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
+  // accumulators are double-buffered across tiles when two sets fit the 512 TMEM columns; the 256-wide two-accumulator
+  // (wavenet) tile uses all 512 columns, so its epilogue and the next tile's MMAs take turns
+  static constexpr int ACC_STAGES = (2 * ACC_COLS <= 512) ? 2 : 1;
+  static constexpr int ACC_STRIDE = (ACC_STAGES == 1) ? 0 : ((ACC_COLS <= 128) ? 128 : 256);
+  static constexpr int TMEM_COLS = (ACC_STAGES == 1) ? 512 : 2 * ACC_STRIDE;
   static constexpr int OFF_STG = STAGES * STAGE_BYTES;
   static constexpr int OFF_BAR = OFF_STG + STG_TOTAL;
   static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
   static_assert(STAGE_BYTES % 1024 == 0, "stage must keep 1024-byte alignment of the swizzled tiles");
-  static_assert(ACC_COLS <= 256, "accumulators of one stage must fit 256 TMEM columns");
+  static_assert(ACC_COLS <= 512, "accumulators of one tile must fit the 512 TMEM columns");
 };
 
 template <int BN, int NACC, int EPI>
@@ -640,8 +643,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
         const int n_tile = tile % p.tiles_n;
         const int bn_eff = (p.n - n_tile * BN) < BN ? (p.n - n_tile * BN) : BN;
         const uint32_t idesc = umma_idesc_f16(2 * BM, bn_eff, /*bf16*/ 1, 0, 0);
-        const uint32_t as = ti & 1;
-        const uint32_t aphase = (ti >> 1) & 1;
+        const uint32_t as = (Cfg::ACC_STAGES == 2) ? (ti & 1) : 0;
+        const uint32_t aphase = (Cfg::ACC_STAGES == 2) ? ((ti >> 1) & 1) : (ti & 1);
         NS2_DBG_STAMP(0);
         mbar_wait(smem_u32(&tempty_bar[as]), aphase ^ 1);
         tc_fence_after();
@@ -681,8 +684,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
     uint32_t ti = 0;
     for (int tile = pair; tile < p.num_tiles; tile += num_pairs, ++ti) {
       const TileCoord t = decode_tile<2 * BM>(p, tile);
-      const uint32_t as = ti & 1;
-      const uint32_t aphase = (ti >> 1) & 1;
+      const uint32_t as = (Cfg::ACC_STAGES == 2) ? (ti & 1) : 0;
+      const uint32_t aphase = (Cfg::ACC_STAGES == 2) ? ((ti >> 1) & 1) : (ti & 1);
       if (ew == 0 && lane == 0) NS2_DBG_STAMP(6);
       mbar_wait(smem_u32(&tfull_bar[as]), aphase);
       tc_fence_after();
@@ -809,7 +812,7 @@ extern "C" int ns2_gemm(const ns2_gemm_args* a, ns2_stream_t stream_) {
   if (out_f32 && a->resid != nullptr && a->resid != a->out) pair = false;
   if (out_f32 && a->resid != nullptr && a->resid_row_stride != a->out_row_stride) pair = false;
   int bn;
-  if (a->epilogue == NS2_EPI_WAVENET) bn = 128;
+  if (a->epilogue == NS2_EPI_WAVENET) bn = (pair && a->n % 256 == 0) ? 256 : 128;
   else if (a->epilogue == NS2_EPI_GEGLU) bn = 256;
   else if (pair) bn = a->n >= 256 ? 256 : 128;
   else bn = (a->n % 256 == 0 && a->n >= 1024) ? 256 : 128;
@@ -881,7 +884,8 @@ extern "C" int ns2_gemm(const ns2_gemm_args* a, ns2_stream_t stream_) {
       case NS2_EPI_GEGLU:
         return launch_gemm2<256, 1, NS2_EPI_GEGLU>(dev, stream);
       case NS2_EPI_WAVENET:
-        return launch_gemm2<128, 2, NS2_EPI_WAVENET>(dev, stream);
+        return bn == 256 ? launch_gemm2<256, 2, NS2_EPI_WAVENET>(dev, stream)
+                         : launch_gemm2<128, 2, NS2_EPI_WAVENET>(dev, stream);
       default:
         return set_error(kErrInvalidArg, "ns2_gemm: unknown epilogue %d", a->epilogue);
     }
