@@ -170,15 +170,27 @@ def rmsnorm_f32(x: torch.Tensor, out: torch.Tensor, gamma: Optional[torch.Tensor
     return out
 
 
+_SMALL_BATCH_MAX = 64          # kMaxSmallBatch in csrc/elementwise.cu
+_SMALL_SMEM_BYTES = 200 * 1024  # dynamic shared memory the small-layer kernel may use for its (batch, k) input tile
+
+
+def _small_chunk(k: int) -> int:
+    return max(1, min(_SMALL_BATCH_MAX, _SMALL_SMEM_BYTES // (4 * k)))
+
+
 def time_cond(times: torch.Tensor, freqs: torch.Tensor, w: torch.Tensor, bias: torch.Tensor,
               out: torch.Tensor) -> torch.Tensor:
-    """out[b] = silu(W @ [t_b, sin(2 pi t_b f), cos(2 pi t_b f)] + bias); out may be a column slice."""
+    """out[b] = silu(W @ [t_b, sin(2 pi t_b f), cos(2 pi t_b f)] + bias); out may be a column slice.
+    Batches larger than the kernel's per-launch limit are processed in row chunks."""
     lib = _lib.load()
     for name, t in (("times", times), ("freqs", freqs), ("w", w), ("bias", bias), ("out", out)):
         _req(t, torch.float32, name)
-    check(lib.ns2_time_cond(times.data_ptr(), times.shape[0], freqs.data_ptr(), freqs.shape[0],
-                            w.data_ptr(), bias.data_ptr(), w.shape[0], out.data_ptr(), out.stride(0),
-                            _stream()), "ns2_time_cond")
+    step = _small_chunk(2 * freqs.shape[0] + 1)
+    for b0 in range(0, times.shape[0], step):
+        tb, ob = times[b0:b0 + step], out[b0:b0 + step]
+        check(lib.ns2_time_cond(tb.data_ptr(), tb.shape[0], freqs.data_ptr(), freqs.shape[0], w.data_ptr(),
+                                bias.data_ptr(), w.shape[0], ob.data_ptr(), out.stride(0), _stream()),
+              "ns2_time_cond")
     return out
 
 
@@ -187,9 +199,11 @@ def small_linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor],
     lib = _lib.load()
     for name, t in (("x", x), ("w", w), ("out", out)):
         _req(t, torch.float32, name)
-    check(lib.ns2_small_linear(x.data_ptr(), x.stride(0), x.shape[0], x.shape[1], w.data_ptr(),
-                               _ptr(bias), w.shape[0], act, out.data_ptr(), out.stride(0), _stream()),
-          "ns2_small_linear")
+    step = _small_chunk(x.shape[1])
+    for b0 in range(0, x.shape[0], step):
+        xb, ob = x[b0:b0 + step], out[b0:b0 + step]
+        check(lib.ns2_small_linear(xb.data_ptr(), x.stride(0), xb.shape[0], x.shape[1], w.data_ptr(), _ptr(bias),
+                                   w.shape[0], act, ob.data_ptr(), out.stride(0), _stream()), "ns2_small_linear")
     return out
 
 

@@ -112,3 +112,14 @@ def test_cuda_graph_replay_matches_eager(name):
     g1b = model(x, times, **kw).clone()
     assert torch.equal(eager, g1) and torch.equal(eager2, g2) and torch.equal(g1, g1b)
     assert len(model._graphs) == 1
+
+
+def test_large_batch_is_chunked_in_the_small_layers():
+    """B > 64 exceeds the per-launch limit of the conditioning-vector kernels; the host splits it (same results)."""
+    _, kwargs, seed = load_model_golden("uncond_small")
+    model = build_model(kwargs, seed, device="cuda")
+    x = torch.randn(96, 128, 128, device="cuda")
+    t = torch.rand(96, device="cuda")
+    full = model(x, t).clone()
+    part = torch.cat([model(x[:48], t[:48]).clone(), model(x[48:], t[48:]).clone()])
+    assert torch.equal(full, part)
