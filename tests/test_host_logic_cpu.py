@@ -137,3 +137,32 @@ def test_rvq_empty_input_returns_empty_tensors():
     assert codes.shape == (0, 8) and codes.dtype == torch.int64 and emb.shape == (0, 128)
     codes, emb = codec.quantize(torch.empty(2, 0, 128))
     assert codes.shape == (2, 0, 8) and emb.shape == (2, 0, 128)
+
+
+def test_conditional_packing_layouts():
+    """Cross-attention K/V weights of all layers are stacked into one matrix; FiLM rows follow the layer order."""
+    _, kwargs, seed = load_model_golden("cond_small")
+    m = build_model(kwargs, seed)
+    P = m._pack()
+    D, inner, depth = m.dim, m.inner, m.depth
+    assert P["x_kv_all"].shape == (depth * 2 * inner, D)
+    for l in range(depth):
+        ref = m.transformer.layers[l][3].to_kv.weight.detach().bfloat16().float()
+        assert torch.allclose(P["x_kv_all"].float()[l * 2 * inner:(l + 1) * 2 * inner], ref)
+        qkv = P[f"l{l}_qkv"].float()
+        assert torch.allclose(qkv[:inner], m.transformer.layers[l][1].to_q.weight.detach().bfloat16().float())
+        assert torch.allclose(qkv[inner:], m.transformer.layers[l][1].to_kv.weight.detach().bfloat16().float())
+    # three adaptive norms per layer when conditional: attn, cross-attn, ff — in that order after the wavenet rows
+    assert m._norms_per_layer == 3
+    G = m.wavenet_layers
+    rows = (m.wavenet_stacks * G + 3 * depth) * 2 * D
+    assert P["film_w"].shape == (rows, m.dim_cond) and P["film_b"].shape == (rows,)
+    off = m._film_tr_off + (1 * 3 + 1) * 2 * D  # layer 1, cross-attn norm
+    ref = m.transformer.layers[1][2].to_gamma_beta.weight.detach().bfloat16().float()
+    assert torch.allclose(P["film_w"].float()[off:off + 2 * D], ref)
+    # perceiver + aligned-condition projection
+    assert P["pr_proj_w"].shape == (D, m.dim_prompt) and P["cond_w"].shape == (D, m.dim_prompt)
+    # skip convs concatenated along K, biases summed
+    last = m.wavenet.stacks[-1]
+    assert P["wn_skip_w"].shape == (D, G * D)
+    assert torch.allclose(P["wn_skip_b"], torch.stack([b.skip_conv.bias for b in last.blocks]).sum(0).detach())
