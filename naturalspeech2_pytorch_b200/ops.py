@@ -61,7 +61,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, n: int, epilogu
     _req(out, out_dtype, "out")
     if out.dim() != 3 or out.shape[0] != a.shape[0] or out.shape[1] != a.shape[1]:
         raise ValueError(f"out must be (batches, rows, *), got {tuple(out.shape)} for a {tuple(a.shape)}")
-    if out.stride(0) != out.shape[1] * out.stride(1):
+    if out.shape[0] > 1 and out.stride(0) != out.shape[1] * out.stride(1):
         raise ValueError("out rows must be uniformly strided across batches")
     if segs is None:
         segs = [(0, 0, a.shape[2], 0, 0)]
@@ -92,7 +92,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, n: int, epilogu
     args.out_row_stride = out.stride(1)
     if resid is not None:
         _req(resid, torch.float32, "resid")
-        if resid.shape != out.shape or resid.stride(0) != resid.shape[1] * resid.stride(1):
+        if resid.shape != out.shape or (resid.shape[0] > 1 and resid.stride(0) != resid.shape[1] * resid.stride(1)):
             raise ValueError("resid must match out's shape with uniformly strided rows")
         args.resid_row_stride = resid.stride(1)
     args.resid = _ptr(resid)
