@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define NS2_ABI_VERSION 1
+#define NS2_ABI_VERSION 2
 
 typedef void* ns2_stream_t; /* cudaStream_t */
 
@@ -108,7 +108,14 @@ typedef struct ns2_attn_args {
   void* out;     int64_t o_row_stride, o_batch_stride;
   int32_t batches, heads, q_len, kv_len, dim_head;
   float scale;
+  int32_t kernel;   /* NS2_ATTN_AUTO, or force one implementation (tests / tuning) */
 } ns2_attn_args;
+
+#define NS2_ATTN_AUTO 0            /* two-tile kernel when q_len > 128 and kv_len > 64, else one-tile */
+#define NS2_ATTN_ONE_TILE 1        /* 128 queries x 64-key tiles per CTA, P staged in shared memory */
+#define NS2_ATTN_TWO_TILE 2        /* persistent, 2 x 128 queries x 128-key tiles, P and O in tensor memory */
+#define NS2_ATTN_TWO_TILE_POLY2 3  /* same, 2 of every 8 exponentials on the FMA pipe (degree-3 polynomial) */
+#define NS2_ATTN_TWO_TILE_POLY4 4  /* same, 4 of every 8 */
 
 int ns2_attn_fwd(const ns2_attn_args* args, ns2_stream_t stream);
 
@@ -156,22 +163,28 @@ int ns2_transpose_cast(const float* x, int32_t batch, int32_t channels, int32_t 
 /* ------------------------------------------------------------------------------------------------
  * 6. Diffusion element-wise steps, fp32 (NaturalSpeech2.forward ns2.py:1621-1666; ddim_sample 1392-1429).
  *    All take per-sample scalars as device arrays of length `batch`; `per_sample` = N*D elements.
- *    ns2_q_sample   : x_t = alpha*x0 + sigma*noise ; target = alpha*noise - sigma*x0   (objective v)
+ *    `objective` selects the parameterisation (ns2.py:1637-1644, 1412-1421): NS2_OBJ_V / NS2_OBJ_EPS / NS2_OBJ_X0.
+ *    ns2_q_sample   : x_t = alpha*x0 + sigma*noise ; target = alpha*noise - sigma*x0 (v) | noise (eps) | x0 (x0)
  *    ns2_mse_rows   : out[b] = mean((pred-target)^2) over the sample          (ns2.py:1646-1647);
  *                     deterministic two-level reduction through caller-provided scratch
- *    ns2_ddim_step  : x0 = alpha*x - sigma*v ; eps = (x - alpha*x0)/max(sigma,1e-10) ;
+ *    ns2_ddim_step  : x0 = alpha*x - sigma*out (v) | (x - sigma*out)/max(alpha,1e-10) (eps) | out (x0) ;
+ *                     eps = (x - alpha*x0)/max(sigma,1e-10) ;
  *                     x <- x0*alpha_next + eps*sigma_next                     (ns2.py:1420-1429)
  *    ns2_cfg_combine: out = null + (cond - null)*scale                        (ns2.py:927)
  * ------------------------------------------------------------------------------------------------ */
 #define NS2_MSE_SCRATCH_PER_SAMPLE 64
+#define NS2_OBJ_V 0
+#define NS2_OBJ_EPS 1
+#define NS2_OBJ_X0 2
 int ns2_q_sample(const float* x0, const float* noise, const float* alpha, const float* sigma,
-                 int32_t batch, int64_t per_sample, float* x_t, float* target, ns2_stream_t stream);
+                 int32_t batch, int64_t per_sample, float* x_t, float* target, int32_t objective,
+                 ns2_stream_t stream);
 int ns2_mse_rows(const float* pred, const float* target, int32_t batch, int64_t per_sample,
                  float* scratch /* batch * NS2_MSE_SCRATCH_PER_SAMPLE floats */, float* out,
                  ns2_stream_t stream);
 int ns2_ddim_step(float* x, const float* v, const float* alpha, const float* sigma,
                   const float* alpha_next, const float* sigma_next, int32_t batch,
-                  int64_t per_sample, ns2_stream_t stream);
+                  int64_t per_sample, int32_t objective, ns2_stream_t stream);
 int ns2_cfg_combine(const float* cond, const float* null_, float scale, int64_t count, float* out,
                     ns2_stream_t stream);
 

@@ -14,7 +14,8 @@ NS2_EPI_BF16, NS2_EPI_F32, NS2_EPI_GEGLU, NS2_EPI_WAVENET = 0, 1, 2, 3
 NS2_GEMM_MAX_SEGS = 8
 NS2_GEMM_MAX_GROUPS = 8
 NS2_MSE_SCRATCH_PER_SAMPLE = 64
-NS2_ABI_VERSION = 1
+NS2_OBJ_V, NS2_OBJ_EPS, NS2_OBJ_X0 = 0, 1, 2
+NS2_ABI_VERSION = 2
 
 
 class GemmSeg(C.Structure):
@@ -45,7 +46,7 @@ class AttnArgs(C.Structure):
         ("v", C.c_void_p), ("v_row_stride", C.c_int64), ("v_batch_stride", C.c_int64),
         ("out", C.c_void_p), ("o_row_stride", C.c_int64), ("o_batch_stride", C.c_int64),
         ("batches", C.c_int32), ("heads", C.c_int32), ("q_len", C.c_int32), ("kv_len", C.c_int32),
-        ("dim_head", C.c_int32), ("scale", C.c_float),
+        ("dim_head", C.c_int32), ("scale", C.c_float), ("kernel", C.c_int32),
     ]
 
 
@@ -65,9 +66,9 @@ SIGNATURES = {
     "ns2_cast_bf16": (C.c_int, [_P, _P, _I64, _P, _P]),
     "ns2_mean_rows": (C.c_int, [_P, _I32, _I32, _I32, _P, _P]),
     "ns2_transpose_cast": (C.c_int, [_P, _I32, _I32, _I32, _P, _P]),
-    "ns2_q_sample": (C.c_int, [_P, _P, _P, _P, _I32, _I64, _P, _P, _P]),
+    "ns2_q_sample": (C.c_int, [_P, _P, _P, _P, _I32, _I64, _P, _P, _I32, _P]),
     "ns2_mse_rows": (C.c_int, [_P, _P, _I32, _I64, _P, _P, _P]),
-    "ns2_ddim_step": (C.c_int, [_P, _P, _P, _P, _P, _P, _I32, _I64, _P]),
+    "ns2_ddim_step": (C.c_int, [_P, _P, _P, _P, _P, _P, _I32, _I64, _I32, _P]),
     "ns2_cfg_combine": (C.c_int, [_P, _P, _F, _I64, _P, _P]),
     "ns2_rvq_prepare": (C.c_int, [_P, _I32, _I32, _I32, _P, _P, _P, _P]),
     "ns2_rvq_encode": (C.c_int, [_P, _I64, _I32, _P, _P, _P, _P, _I32, _I32, _P, _P, _P]),

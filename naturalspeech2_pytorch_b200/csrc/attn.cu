@@ -304,6 +304,414 @@ __global__ void __launch_bounds__(192, 2) attn_fwd_kernel(const __grid_constant_
   }
 }
 
+
+// =====================================================================================================
+// Two-tile kernel (the self-attention path): persistent CTAs, 320 threads.
+//   warps 0-3   softmax warpgroup 0: query rows [q0, q0+128) of the work item, thread r <-> TMEM lane r
+//   warps 4-7   softmax warpgroup 1: query rows [q0+128, q0+256)
+//   warp 8      TMA producer: Q pair (double-buffered across work items) + K_j/V_j tiles (128 keys) through a ring
+//   warp 9      tcgen05.mma issuer
+// Per 128-key tile and warpgroup w:  S^w = Q^w K_j^T (SS MMA, fp32 in TMEM) -> the warpgroup reads its 128 scores into
+// registers (S is free again at once, so S^w_{j+1} is computed while the exponentials of tile j are evaluated) ->
+// row max with LAZY rescaling (the running max only moves when it grows by > 2^8; the accumulator in TMEM is rescaled
+// in place by the row's own thread in that rare case) -> P = exp2(s*c - m) packed to bf16 and written back to TENSOR
+// MEMORY (tcgen05.st) -> O^w += P V_j with P as the TMEM A operand and V the MN-major B operand, accumulating in TMEM
+// across all key tiles.  The tensor core is never on the softmax warps' critical path after the first tile; the kernel
+// runs at the rate the two warpgroups evaluate exponentials (MUFU ex2 + an FMA-pipe polynomial for POLY of every 8).
+// TMEM columns: S0 [0,128) S1 [128,256) O0 [256,320) O1 [320,384) P0 [384,448) P1 [448,512).
+// =====================================================================================================
+namespace attn2 {
+constexpr int BQ = 128;      // query rows per warpgroup
+constexpr int BKV = 128;     // keys per tile
+constexpr int DH = 64;
+constexpr int KVS = 4;       // K/V ring depth
+constexpr int Q_BYTES = BQ * DH * 2;          // 16 KB per query tile
+constexpr int KV_BYTES = BKV * DH * 2;        // 16 KB each for K and V
+constexpr int OFF_Q = 0;                               // [2 stages][2 tiles]
+constexpr int OFF_K = OFF_Q + 4 * Q_BYTES;             // [KVS]
+constexpr int OFF_V = OFF_K + KVS * KV_BYTES;          // [KVS]
+constexpr int OFF_BAR = OFF_V + KVS * KV_BYTES;
+constexpr int SMEM_BYTES = OFF_BAR + 256;              // 192.25 KB -> one CTA per SM
+constexpr int TM_S = 0, TM_O = 256, TM_P = 384;
+constexpr int THREADS = 384;     // 2 softmax warpgroups + 1 auxiliary warpgroup (TMA warp, MMA warp, 2 idle)
+constexpr float LAZY = 8.0f;  // log2 units
+}  // namespace attn2
+
+struct Attn2Dev {
+  CUtensorMap tmQ, tmK, tmV;
+  __nv_bfloat16* out;
+  long long o_rs, o_bs;
+  int q_len, kv_len, heads;
+  int q_pairs, num_items;
+  float scale_log2e;
+};
+
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
+__device__ __forceinline__ unsigned long long pack_f32x2(float lo, float hi) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack_f32x2(unsigned long long v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long fma_f32x2(unsigned long long a, unsigned long long b,
+                                                        unsigned long long c) {
+  unsigned long long r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ unsigned long long add_f32x2(unsigned long long a, unsigned long long b) {
+  unsigned long long r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint32_t cvt_bf16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+
+// 2^x for a pair on the FMA pipe (Cody-Waite: n = round(x), f = x - n in [-0.5, 0.5], degree-3 minimax polynomial for
+// 2^f, exponent patched with integer adds).  Inputs must be >= -125 (callers clamp); relative error 1.1e-4, far below
+// the bf16 rounding (2^-9) applied to the result.
+__device__ __forceinline__ void exp2_poly_x2(unsigned long long x, float& y0, float& y1) {
+  const unsigned long long magic = pack_f32x2(12582912.0f, 12582912.0f);  // 1.5 * 2^23
+  const unsigned long long neg1 = pack_f32x2(-1.0f, -1.0f);
+  const unsigned long long t = add_f32x2(x, magic);          // integer part in the low mantissa bits
+  const unsigned long long n = fma_f32x2(magic, neg1, t);    // n = t - magic
+  const unsigned long long f = fma_f32x2(n, neg1, x);        // f = x - n
+  unsigned long long p = fma_f32x2(pack_f32x2(0.05550410866f, 0.05550410866f), f,
+                                   pack_f32x2(0.24022650696f, 0.24022650696f));
+  p = fma_f32x2(p, f, pack_f32x2(0.69314718056f, 0.69314718056f));
+  p = fma_f32x2(p, f, pack_f32x2(1.0f, 1.0f));
+  float p0, p1, t0, t1;
+  unpack_f32x2(p, p0, p1);
+  unpack_f32x2(t, t0, t1);
+  y0 = __uint_as_float(__float_as_uint(p0) + (__float_as_uint(t0) << 23));
+  y1 = __uint_as_float(__float_as_uint(p1) + (__float_as_uint(t1) << 23));
+}
+
+// POLY: how many of every 8 consecutive exponentials are evaluated on the FMA pipe instead of MUFU (0, 2 or 4)
+template <int POLY>
+__global__ void __launch_bounds__(attn2::THREADS, 1) attn2_fwd_kernel(const __grid_constant__ Attn2Dev p) {
+  using namespace attn2;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+  uint64_t* q_full = bars + 0;              // [2]
+  uint64_t* q_empty = bars + 2;             // [2]
+  uint64_t* kv_full = bars + 4;             // [KVS]
+  uint64_t* kv_empty = bars + 4 + KVS;      // [KVS]
+  uint64_t* s_full = bars + 4 + 2 * KVS;    // [2] MMA -> softmax: S^w ready
+  uint64_t* s_free = bars + 6 + 2 * KVS;    // [2] softmax -> MMA: S^w is in registers (4 warp arrivals)
+  uint64_t* p_full = bars + 8 + 2 * KVS;    // [2] softmax -> MMA: P^w is in TMEM (4 warp arrivals)
+  uint64_t* o_full = bars + 10 + 2 * KVS;   // [2] MMA -> softmax: O^w += P^w V complete
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 12 + 2 * KVS);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int T = (p.kv_len + BKV - 1) / BKV;
+  const int my_items = (p.num_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) /
+                       static_cast<int>(gridDim.x);
+
+  if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) {
+    printf("ns2 attn2: dynamic shared memory is not 1024-byte aligned\n");
+    __trap();
+  }
+  if (warp == 8 && lane == 0) {
+    tma_prefetch_desc(&p.tmQ);
+    tma_prefetch_desc(&p.tmK);
+    tma_prefetch_desc(&p.tmV);
+  }
+  if (warp == 9 && lane == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(&q_full[i]), 1);
+      mbar_init(smem_u32(&q_empty[i]), 1);
+      mbar_init(smem_u32(&s_full[i]), 1);
+      mbar_init(smem_u32(&s_free[i]), 4);
+      mbar_init(smem_u32(&p_full[i]), 4);
+      mbar_init(smem_u32(&o_full[i]), 1);
+    }
+    for (int i = 0; i < KVS; ++i) {
+      mbar_init(smem_u32(&kv_full[i]), 1);
+      mbar_init(smem_u32(&kv_empty[i]), 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 8) tmem_alloc(smem_u32(tmem_holder), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  auto decode = [&](int it, int& b, int& head, int& q0) {
+    const int item = static_cast<int>(blockIdx.x) + it * static_cast<int>(gridDim.x);
+    const int qp = item % p.q_pairs;
+    const int bh = item / p.q_pairs;
+    head = bh % p.heads;
+    b = bh / p.heads;
+    q0 = qp * 2 * BQ;
+  };
+
+  // register budget (setmaxnreg): the softmax warpgroups keep a whole 128-score row and its packed probabilities in
+  // registers; the auxiliary warpgroup gives its share up
+  if (warp >= 8) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    if (warp == 8) {
+    // ================================ TMA producer ================================
+    if (lane == 0) {
+      uint32_t g = 0;  // global key-tile counter of this CTA
+      for (int it = 0; it < my_items; ++it) {
+        int b, head, q0;
+        decode(it, b, head, q0);
+        const int qs = it & 1;
+        mbar_wait(smem_u32(&q_empty[qs]), ((it >> 1) & 1) ^ 1);
+        const uint32_t qb = smem_u32(&q_full[qs]);
+        mbar_arrive_expect_tx(qb, 2 * Q_BYTES);
+        tma_load_3d(smem_u32(smem + OFF_Q + (qs * 2 + 0) * Q_BYTES), &p.tmQ, qb, head * DH, q0, b);
+        tma_load_3d(smem_u32(smem + OFF_Q + (qs * 2 + 1) * Q_BYTES), &p.tmQ, qb, head * DH, q0 + BQ, b);
+        for (int j = 0; j < T; ++j, ++g) {
+          const int st = g % KVS;
+          mbar_wait(smem_u32(&kv_empty[st]), ((g / KVS) & 1) ^ 1);
+          const uint32_t fb = smem_u32(&kv_full[st]);
+          mbar_arrive_expect_tx(fb, 2 * KV_BYTES);
+          tma_load_3d(smem_u32(smem + OFF_K + st * KV_BYTES), &p.tmK, fb, head * DH, j * BKV, b);
+          tma_load_3d(smem_u32(smem + OFF_V + st * KV_BYTES), &p.tmV, fb, head * DH, j * BKV, b);
+        }
+      }
+    }
+    } else if (warp == 9) {
+    // ================================ MMA issuer ==================================
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = umma_idesc_f16(BQ, BKV, 1, 0, 0);
+      constexpr uint32_t idesc_o = umma_idesc_f16(BQ, DH, 1, 0, /*V is MN-major*/ 1);
+      const int total = my_items * T;
+      // S for global tile gs (item gs / T, key tile gs % T), both warpgroups
+      auto issue_s = [&](int gs) {
+        const int it = gs / T, j = gs - it * T;
+        const int qs = it & 1;
+        if (j == 0) {
+          mbar_wait(smem_u32(&q_full[qs]), (it >> 1) & 1);
+        }
+        const int st = gs % KVS;
+        mbar_wait(smem_u32(&kv_full[st]), (gs / KVS) & 1);
+        tc_fence_after();
+        const uint64_t dk = umma_desc_sw128(smem_u32(smem + OFF_K + st * KV_BYTES), 16, 1024);
+#pragma unroll
+        for (int w = 0; w < 2; ++w) {
+          if (gs > 0) {  // the warpgroup has pulled S^w of the previous tile into registers
+            mbar_wait(smem_u32(&s_free[w]), (gs - 1) & 1);
+            tc_fence_after();
+          }
+          const uint64_t dq = umma_desc_sw128(smem_u32(smem + OFF_Q + (qs * 2 + w) * Q_BYTES), 16, 1024);
+#pragma unroll
+          for (int k = 0; k < DH / 16; ++k)
+            tc_mma_f16(tmem_base + TM_S + w * BKV, dq + 2 * k, dk + 2 * k, idesc_s, k > 0);
+          tc_commit(smem_u32(&s_full[w]));
+        }
+        if (j == T - 1) tc_commit(smem_u32(&q_empty[qs]));  // every S of this item has been issued
+      };
+      if (total > 0) issue_s(0);
+      for (int g = 0; g < total; ++g) {
+        if (g + 1 < total) issue_s(g + 1);
+        const int j = g % T;
+        const int st = g % KVS;
+        const uint32_t vbase = smem_u32(smem + OFF_V + st * KV_BYTES);
+#pragma unroll
+        for (int w = 0; w < 2; ++w) {
+          mbar_wait(smem_u32(&p_full[w]), g & 1);
+          tc_fence_after();
+#pragma unroll
+          for (int k = 0; k < BKV / 16; ++k) {
+            // A = P^w from TMEM: 16 keys = 8 packed columns per step; B = V: 16 keys = 2048 bytes per step
+            const uint64_t dv = umma_desc_sw128(vbase + k * 2048, 1024, 1024);
+            tc_mma_f16_ts(tmem_base + TM_O + w * DH, tmem_base + TM_P + w * (BKV / 2) + k * 8, dv, idesc_o,
+                          (j > 0) | (k > 0));
+          }
+          tc_commit(smem_u32(&o_full[w]));
+        }
+        tc_commit(smem_u32(&kv_empty[st]));
+      }
+    }
+    }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
+    // ================================ softmax warpgroups ==========================
+    const int w = warp >> 2;                      // warpgroup = query tile
+    const int qw = warp & 3;                      // TMEM lane quarter
+    const int row = qw * 32 + lane;               // row inside the 128-row tile
+    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(qw * 32) << 16);
+    const uint32_t s_addr = lane_addr + TM_S + w * BKV;
+    const uint32_t o_addr = lane_addr + TM_O + w * DH;
+    const uint32_t p_addr = lane_addr + TM_P + w * (BKV / 2);
+    const float c = p.scale_log2e;
+    const unsigned long long c2 = pack_f32x2(c, c);
+    uint32_t g = 0;
+    for (int it = 0; it < my_items; ++it) {
+      int b, head, q0;
+      decode(it, b, head, q0);
+      float m_run = -INFINITY, l_run = 0.f;
+      for (int j = 0; j < T; ++j, ++g) {
+        mbar_wait(smem_u32(&s_full[w]), g & 1);
+        tc_fence_after();
+        float s[BKV];
+        {
+          uint32_t r0[32], r1[32], r2[32], r3[32];
+          tmem_ld32(s_addr, r0);
+          tmem_ld32(s_addr + 32, r1);
+          tmem_ld32(s_addr + 64, r2);
+          tmem_ld32(s_addr + 96, r3);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            s[i] = __uint_as_float(r0[i]);
+            s[32 + i] = __uint_as_float(r1[i]);
+            s[64 + i] = __uint_as_float(r2[i]);
+            s[96 + i] = __uint_as_float(r3[i]);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&s_free[w]));   // S^w may be overwritten by the next tile's MMA
+        const int valid = p.kv_len - j * BKV;
+        if (valid < BKV) {  // padding keys of the last tile (TMA zero-filled): exclude them
+#pragma unroll
+          for (int i = 0; i < BKV; ++i)
+            if (i >= valid) s[i] = -INFINITY;
+        }
+        float m0 = s[0], m1 = s[1], m2 = s[2], m3 = s[3];
+#pragma unroll
+        for (int i = 4; i < BKV; i += 8) {
+          m0 = fmax3(m0, s[i], s[i + 1]);
+          m1 = fmax3(m1, s[i + 2], s[i + 3]);
+          if (i + 4 < BKV) {
+            m2 = fmax3(m2, s[i + 4], s[i + 5]);
+            m3 = fmax3(m3, s[i + 6], s[i + 7]);
+          }
+        }
+        const float m_tile = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) * c;
+        // lazy rescaling: keep the stale maximum unless the true one exceeds it by more than 2^LAZY
+        const bool grow = m_tile > m_run + LAZY;
+        if (__any_sync(0xffffffffu, grow && j > 0)) {
+          // rare: rescale this row's accumulator in TMEM (needs the previous P.V to have completed)
+          mbar_wait(smem_u32(&o_full[w]), (g - 1) & 1);
+          tc_fence_after();
+          const float a = grow ? exp2f(m_run - m_tile) : 1.0f;
+#pragma unroll 1
+          for (int cc = 0; cc < DH; cc += 16) {   // 16 columns at a time: the 128 scores stay live in registers
+            uint32_t o[16];
+            tmem_ld16(o_addr + cc, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * a);
+            tmem_st16(o_addr + cc, o);
+          }
+          tmem_st_wait();
+          if (grow) {
+            l_run *= a;
+            m_run = m_tile;
+          }
+        } else if (grow) {  // first tile of the item: nothing accumulated yet
+          m_run = m_tile;
+          l_run = 0.f;
+        }
+        // P = exp2(s*c - m) -> bf16 pairs; row sum in fp32
+        const unsigned long long nm2 = pack_f32x2(-m_run, -m_run);
+        unsigned long long lsum0 = 0ull, lsum1 = 0ull;  // two packed (0.f, 0.f) accumulators
+        uint32_t pk_lo[32], pk_hi[32];   // packed bf16 pairs of keys [0,64) and [64,128)
+#pragma unroll
+        for (int i = 0; i < BKV; i += 8) {
+          float e[8];
+#pragma unroll
+          for (int q = 0; q < 8; q += 2) {
+            unsigned long long x = fma_f32x2(pack_f32x2(s[i + q], s[i + q + 1]), c2, nm2);
+            if (q < POLY) {
+              float x0, x1;
+              unpack_f32x2(x, x0, x1);
+              x = pack_f32x2(fmaxf(x0, -125.0f), fmaxf(x1, -125.0f));
+              exp2_poly_x2(x, e[q], e[q + 1]);
+            } else {
+              float x0, x1;
+              unpack_f32x2(x, x0, x1);
+              e[q] = ex2_approx(x0);
+              e[q + 1] = ex2_approx(x1);
+            }
+          }
+          lsum0 = add_f32x2(lsum0, pack_f32x2(e[0], e[1]));
+          lsum1 = add_f32x2(lsum1, pack_f32x2(e[2], e[3]));
+          lsum0 = add_f32x2(lsum0, pack_f32x2(e[4], e[5]));
+          lsum1 = add_f32x2(lsum1, pack_f32x2(e[6], e[7]));
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint32_t v = cvt_bf16x2(e[2 * q], e[2 * q + 1]);
+            if (i < BKV / 2) pk_lo[i / 2 + q] = v;
+            else pk_hi[(i - BKV / 2) / 2 + q] = v;
+          }
+        }
+        {
+          float a0, a1, b0, b1;
+          unpack_f32x2(lsum0, a0, a1);
+          unpack_f32x2(lsum1, b0, b1);
+          l_run += (a0 + a1) + (b0 + b1);
+        }
+        // the P buffer is still being read by the previous tile's P.V until o_full flips
+        if (j > 0) {
+          mbar_wait(smem_u32(&o_full[w]), (g - 1) & 1);
+          tc_fence_after();
+        }
+        tmem_st32(p_addr, pk_lo);
+        tmem_st32(p_addr + 32, pk_hi);
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&p_full[w]));
+      }
+      // ---- epilogue of the work item: O / l -> bf16 -> global ----
+      mbar_wait(smem_u32(&o_full[w]), (g - 1) & 1);
+      tc_fence_after();
+      uint32_t o0[32], o1[32];
+      tmem_ld32(o_addr, o0);
+      tmem_ld32(o_addr + 32, o1);
+      tmem_ld_wait();
+      const int qrow = q0 + w * BQ + row;
+      if (qrow < p.q_len) {
+        const float inv = 1.0f / l_run;
+        __nv_bfloat16* op = p.out + static_cast<long long>(b) * p.o_bs + static_cast<long long>(qrow) * p.o_rs +
+                            head * DH;
+        uint4* o4 = reinterpret_cast<uint4*>(op);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          uint4 v;
+          v.x = pack_bf16x2(__uint_as_float(o0[8 * i + 0]) * inv, __uint_as_float(o0[8 * i + 1]) * inv);
+          v.y = pack_bf16x2(__uint_as_float(o0[8 * i + 2]) * inv, __uint_as_float(o0[8 * i + 3]) * inv);
+          v.z = pack_bf16x2(__uint_as_float(o0[8 * i + 4]) * inv, __uint_as_float(o0[8 * i + 5]) * inv);
+          v.w = pack_bf16x2(__uint_as_float(o0[8 * i + 6]) * inv, __uint_as_float(o0[8 * i + 7]) * inv);
+          o4[i] = v;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          uint4 v;
+          v.x = pack_bf16x2(__uint_as_float(o1[8 * i + 0]) * inv, __uint_as_float(o1[8 * i + 1]) * inv);
+          v.y = pack_bf16x2(__uint_as_float(o1[8 * i + 2]) * inv, __uint_as_float(o1[8 * i + 3]) * inv);
+          v.z = pack_bf16x2(__uint_as_float(o1[8 * i + 4]) * inv, __uint_as_float(o1[8 * i + 5]) * inv);
+          v.w = pack_bf16x2(__uint_as_float(o1[8 * i + 6]) * inv, __uint_as_float(o1[8 * i + 7]) * inv);
+          o4[4 + i] = v;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 }  // namespace ns2
 
 extern "C" int ns2_attn_fwd(const ns2_attn_args* a, ns2_stream_t stream_) {
@@ -341,14 +749,58 @@ extern "C" int ns2_attn_fwd(const ns2_attn_args* a, ns2_stream_t stream_) {
   dev.kv_len = a->kv_len;
   dev.scale_log2e = a->scale * 1.4426950408889634f;
 
-  static bool configured = false;
-  if (!configured) {
-    NS2_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        attn::SMEM_BYTES));
-    configured = true;
+  // kernel choice: the two-tile kernel (256 queries x 128-key tiles per CTA, P and O in TMEM) for self-attention sized
+  // problems; the single-tile kernel (128 queries x 64-key tiles) for short key sequences (cross attention over the 32
+  // perceiver latents) and short query sequences (the perceiver itself).  args->kernel overrides (tests, tuning).
+  int kernel = a->kernel;
+  if (kernel == NS2_ATTN_AUTO) kernel = (a->kv_len > 64 && a->q_len > 128) ? NS2_ATTN_TWO_TILE : NS2_ATTN_ONE_TILE;
+  NS2_REQUIRE(kernel == NS2_ATTN_ONE_TILE || kernel == NS2_ATTN_TWO_TILE || kernel == NS2_ATTN_TWO_TILE_POLY2 ||
+                  kernel == NS2_ATTN_TWO_TILE_POLY4,
+              "attn_fwd: unknown kernel selector %d", a->kernel);
+  if (kernel == NS2_ATTN_ONE_TILE) {
+    NS2_CUDA_CHECK(set_max_smem_once(attn_fwd_kernel, attn::SMEM_BYTES));
+    dim3 grid((a->q_len + attn::BQ - 1) / attn::BQ, a->heads, a->batches);
+    attn_fwd_kernel<<<grid, 192, attn::SMEM_BYTES, stream>>>(dev);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    NS2_CUDA_CHECK(cudaGetLastError());
+    return kOk;
   }
-  dim3 grid((a->q_len + attn::BQ - 1) / attn::BQ, a->heads, a->batches);
-  attn_fwd_kernel<<<grid, 192, attn::SMEM_BYTES, stream>>>(dev);
+  Attn2Dev d2;
+  memset(&d2, 0, sizeof(d2));
+  {
+    const uint32_t box2[3] = {64, attn2::BQ, 1};   // Q tiles and K/V tiles are all 128 rows x 64 columns
+    const uint64_t qdims[3] = {(uint64_t)a->heads * 64, (uint64_t)a->q_len, (uint64_t)a->batches};
+    const uint64_t qstr[3] = {2, (uint64_t)a->q_row_stride * 2, (uint64_t)a->q_batch_stride * 2};
+    int rc = make_tmap_16bit(&d2.tmQ, a->q, 3, qdims, qstr, box2);
+    if (rc != kOk) return rc;
+    const uint64_t kdims[3] = {(uint64_t)a->heads * 64, (uint64_t)a->kv_len, (uint64_t)a->batches};
+    const uint64_t kstr[3] = {2, (uint64_t)a->k_row_stride * 2, (uint64_t)a->k_batch_stride * 2};
+    const uint64_t vstr[3] = {2, (uint64_t)a->v_row_stride * 2, (uint64_t)a->v_batch_stride * 2};
+    rc = make_tmap_16bit(&d2.tmK, a->k, 3, kdims, kstr, box2);
+    if (rc != kOk) return rc;
+    rc = make_tmap_16bit(&d2.tmV, a->v, 3, kdims, vstr, box2);
+    if (rc != kOk) return rc;
+  }
+  d2.out = reinterpret_cast<__nv_bfloat16*>(a->out);
+  d2.o_rs = a->o_row_stride;
+  d2.o_bs = a->o_batch_stride;
+  d2.q_len = a->q_len;
+  d2.kv_len = a->kv_len;
+  d2.heads = a->heads;
+  d2.q_pairs = (a->q_len + 2 * attn2::BQ - 1) / (2 * attn2::BQ);
+  d2.num_items = d2.q_pairs * a->heads * a->batches;
+  d2.scale_log2e = a->scale * 1.4426950408889634f;
+  const int grid2 = d2.num_items < num_sms() ? d2.num_items : num_sms();
+  if (kernel == NS2_ATTN_TWO_TILE) {
+    NS2_CUDA_CHECK(set_max_smem_once(attn2_fwd_kernel<0>, attn2::SMEM_BYTES));
+    attn2_fwd_kernel<0><<<grid2, attn2::THREADS, attn2::SMEM_BYTES, stream>>>(d2);
+  } else if (kernel == NS2_ATTN_TWO_TILE_POLY2) {
+    NS2_CUDA_CHECK(set_max_smem_once(attn2_fwd_kernel<2>, attn2::SMEM_BYTES));
+    attn2_fwd_kernel<2><<<grid2, attn2::THREADS, attn2::SMEM_BYTES, stream>>>(d2);
+  } else {
+    NS2_CUDA_CHECK(set_max_smem_once(attn2_fwd_kernel<4>, attn2::SMEM_BYTES));
+    attn2_fwd_kernel<4><<<grid2, attn2::THREADS, attn2::SMEM_BYTES, stream>>>(d2);
+  }
   g_launches.fetch_add(1, std::memory_order_relaxed);
   NS2_CUDA_CHECK(cudaGetLastError());
   return kOk;

@@ -209,7 +209,7 @@ __global__ void __launch_bounds__(256) q_sample_kernel(const float4* __restrict_
                                                        const float* __restrict__ alpha,
                                                        const float* __restrict__ sigma,
                                                        long long per4, float4* __restrict__ xt,
-                                                       float4* __restrict__ target) {
+                                                       float4* __restrict__ target, int objective) {
   const int b = blockIdx.y;
   const float a = alpha[b], s = sigma[b];
   const long long base = static_cast<long long>(b) * per4;
@@ -217,9 +217,13 @@ __global__ void __launch_bounds__(256) q_sample_kernel(const float4* __restrict_
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const float4 x = __ldg(x0 + base + i), e = __ldg(noise + base + i);
     xt[base + i] = make_float4(a * x.x + s * e.x, a * x.y + s * e.y, a * x.z + s * e.z, a * x.w + s * e.w);
-    if (target != nullptr)
-      target[base + i] =
-          make_float4(a * e.x - s * x.x, a * e.y - s * x.y, a * e.z - s * x.z, a * e.w - s * x.w);
+    if (target != nullptr) {  // ns2.py:1637-1644
+      if (objective == NS2_OBJ_V)
+        target[base + i] =
+            make_float4(a * e.x - s * x.x, a * e.y - s * x.y, a * e.z - s * x.z, a * e.w - s * x.w);
+      else
+        target[base + i] = (objective == NS2_OBJ_EPS) ? e : x;
+    }
   }
 }
 
@@ -264,13 +268,16 @@ __global__ void __launch_bounds__(256) ddim_step_kernel(float4* __restrict__ x,
                                                         const float* __restrict__ sigma,
                                                         const float* __restrict__ alpha_next,
                                                         const float* __restrict__ sigma_next,
-                                                        long long per4) {
+                                                        long long per4, int objective) {
   const int b = blockIdx.y;
   const float a = alpha[b], s = sigma[b], an = alpha_next[b], sn = sigma_next[b];
   const float s_safe = fmaxf(s, 1e-10f);  // safe_div (ns2.py:1122-1123)
+  const float a_safe = fmaxf(a, 1e-10f);
   const long long base = static_cast<long long>(b) * per4;
   auto upd = [&](float xv, float vv) {
-    const float x0 = a * xv - s * vv;           // ns2.py:1421
+    // x_start from the model output (ns2.py:1412-1421): v / eps / x0 parameterisation
+    const float x0 = objective == NS2_OBJ_V ? a * xv - s * vv
+                                            : (objective == NS2_OBJ_EPS ? (xv - s * vv) / a_safe : vv);
     const float eps = (xv - a * x0) / s_safe;   // ns2.py:1425
     return x0 * an + eps * sn;                  // ns2.py:1429
   };
@@ -292,14 +299,7 @@ __global__ void __launch_bounds__(256) cfg_combine_kernel(const float4* __restri
   }
 }
 
-static cudaError_t configure_small_linear() {
-  static bool configured = false;
-  if (configured) return cudaSuccess;
-  cudaError_t e = cudaFuncSetAttribute(small_linear_kernel,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-  configured = (e == cudaSuccess);
-  return e;
-}
+static cudaError_t configure_small_linear() { return set_max_smem_once(small_linear_kernel, 200 * 1024); }
 
 static unsigned grid_for(long long n4) {
   long long g = (n4 + 255) / 256;
@@ -398,13 +398,15 @@ int ns2_transpose_cast(const float* x, int32_t batch, int32_t channels, int32_t 
 }
 
 int ns2_q_sample(const float* x0, const float* noise, const float* alpha, const float* sigma,
-                 int32_t batch, int64_t per_sample, float* x_t, float* target, ns2_stream_t stream) {
+                 int32_t batch, int64_t per_sample, float* x_t, float* target, int32_t objective,
+                 ns2_stream_t stream) {
   NS2_REQUIRE(x0 && noise && alpha && sigma && x_t, "q_sample: NULL pointer");
+  NS2_REQUIRE(objective >= NS2_OBJ_V && objective <= NS2_OBJ_X0, "q_sample: unknown objective %d", objective);
   NS2_REQUIRE(per_sample % 4 == 0 && batch > 0, "q_sample: per_sample must be a multiple of 4");
   dim3 grid(grid_for(per_sample / 4) / (batch > 8 ? 4 : 1) + 1, batch);
   q_sample_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const float4*>(x0), reinterpret_cast<const float4*>(noise), alpha, sigma,
-      per_sample / 4, reinterpret_cast<float4*>(x_t), reinterpret_cast<float4*>(target));
+      per_sample / 4, reinterpret_cast<float4*>(x_t), reinterpret_cast<float4*>(target), objective);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   NS2_CUDA_CHECK(cudaGetLastError());
   return kOk;
@@ -426,13 +428,14 @@ int ns2_mse_rows(const float* pred, const float* target, int32_t batch, int64_t 
 
 int ns2_ddim_step(float* x, const float* v, const float* alpha, const float* sigma,
                   const float* alpha_next, const float* sigma_next, int32_t batch,
-                  int64_t per_sample, ns2_stream_t stream) {
+                  int64_t per_sample, int32_t objective, ns2_stream_t stream) {
   NS2_REQUIRE(x && v && alpha && sigma && alpha_next && sigma_next, "ddim_step: NULL pointer");
+  NS2_REQUIRE(objective >= NS2_OBJ_V && objective <= NS2_OBJ_X0, "ddim_step: unknown objective %d", objective);
   NS2_REQUIRE(per_sample % 4 == 0 && batch > 0, "ddim_step: per_sample must be a multiple of 4");
   dim3 grid(grid_for(per_sample / 4) / (batch > 8 ? 4 : 1) + 1, batch);
   ddim_step_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<float4*>(x), reinterpret_cast<const float4*>(v), alpha, sigma, alpha_next,
-      sigma_next, per_sample / 4);
+      sigma_next, per_sample / 4, objective);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   NS2_CUDA_CHECK(cudaGetLastError());
   return kOk;

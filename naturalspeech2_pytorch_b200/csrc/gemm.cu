@@ -718,13 +718,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
 template <int BN, int NACC, int EPI>
 static int launch_gemm(const GemmDev& dev, cudaStream_t stream) {
   using Cfg = GemmCfg<BN, NACC>;
-  static bool configured = false;
   auto kern = gemm_kernel<BN, NACC, EPI>;
-  if (!configured) {
-    NS2_CUDA_CHECK(
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    configured = true;
-  }
+  NS2_CUDA_CHECK(set_max_smem_once(kern, Cfg::SMEM_BYTES));
   const int grid = dev.num_tiles < num_sms() ? dev.num_tiles : num_sms();
   kern<<<grid, 256, Cfg::SMEM_BYTES, stream>>>(dev);
   g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -735,13 +730,8 @@ static int launch_gemm(const GemmDev& dev, cudaStream_t stream) {
 template <int BN, int NACC, int EPI>
 static int launch_gemm2(const GemmDev& dev, cudaStream_t stream) {
   using Cfg = Gemm2Cfg<BN, NACC>;
-  static bool configured = false;
   auto kern = gemm2_kernel<BN, NACC, EPI>;
-  if (!configured) {
-    NS2_CUDA_CHECK(
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    configured = true;
-  }
+  NS2_CUDA_CHECK(set_max_smem_once(kern, Cfg::SMEM_BYTES));
   int pairs = num_sms() / 2;
   if (dev.num_tiles < pairs) pairs = dev.num_tiles;
   kern<<<2 * pairs, 256, Cfg::SMEM_BYTES, stream>>>(dev);  // __cluster_dims__(2,1,1)

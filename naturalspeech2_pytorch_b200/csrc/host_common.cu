@@ -2,8 +2,11 @@
 #include "../../include/ns2_b200.h"
 
 #include <cudaTypedefs.h>
+#include <atomic>
 #include <mutex>
 #include <string.h>
+#include <utility>
+#include <vector>
 
 namespace ns2 {
 
@@ -73,15 +76,32 @@ int make_tmap_f32(CUtensorMap* out, const void* base, int rank, const uint64_t* 
   return make_tmap(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, base, rank, dims, strides_bytes, box);
 }
 
+constexpr int kMaxDevices = 64;
+
 int num_sms() {
-  static int n = 0;
+  static std::atomic<int> cache[kMaxDevices];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return 148;
+  int n = cache[dev].load(std::memory_order_relaxed);
   if (n == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
-    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
-      n = 148;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cache[dev].store(n, std::memory_order_relaxed);
   }
   return n;
+}
+
+cudaError_t set_max_smem_once_impl(const void* kernel, int bytes) {
+  static std::mutex mu;
+  static std::vector<std::pair<const void*, int>> done;  // (kernel, device) pairs already configured
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  std::lock_guard<std::mutex> lock(mu);
+  for (const auto& d : done)
+    if (d.first == kernel && d.second == dev) return cudaSuccess;
+  e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) done.emplace_back(kernel, dev);
+  return e;
 }
 
 }  // namespace ns2

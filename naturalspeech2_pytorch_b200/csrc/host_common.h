@@ -43,6 +43,15 @@ int make_tmap_f32(CUtensorMap* out, const void* base, int rank, const uint64_t* 
     if (!(cond)) return ns2::set_error(ns2::kErrInvalidArg, __VA_ARGS__);                     \
   } while (0)
 
+// SM count of the CURRENT device (cached per device ordinal).
 int num_sms();
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (kernel, device): the attribute is per device, so a
+// process that drives several GPUs must opt in on each of them.
+cudaError_t set_max_smem_once_impl(const void* kernel, int bytes);
+template <typename K>
+inline cudaError_t set_max_smem_once(K kernel, int bytes) {
+  return set_max_smem_once_impl(reinterpret_cast<const void*>(kernel), bytes);
+}
 
 }  // namespace ns2

@@ -626,12 +626,7 @@ int ns2_rvq_encode(const float* frames, int64_t num_frames, int32_t d, const flo
   dev.num_frames = num_frames;
   dev.Q = q;
   dev.K = k;
-  static bool configured = false;
-  if (!configured) {
-    NS2_CUDA_CHECK(cudaFuncSetAttribute(rvq_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        rvq::SMEM_BYTES));
-    configured = true;
-  }
+  NS2_CUDA_CHECK(set_max_smem_once(rvq_encode_kernel, rvq::SMEM_BYTES));
   const long long grid = (num_frames + rvq::BF - 1) / rvq::BF;
   NS2_REQUIRE(grid <= 0x7fffffffLL, "rvq_encode: too many frames");
   rvq_encode_kernel<<<static_cast<unsigned>(grid), 320, rvq::SMEM_BYTES,

@@ -74,8 +74,6 @@ class NaturalSpeech2(nn.Module):
             f"transformer model dimension {model.dim} must be equal to codec dimension {codec.codebook_dim}"
         self.dim = codec.codebook_dim if _exists(codec) else model.dim
         assert objective in {"x0", "eps", "v"}
-        if objective != "v":
-            raise NotImplementedError("only the default 'v' objective is implemented on the sm_100a kernels")
         self.objective = objective
         sched = {"linear": simple_linear_schedule, "cosine": cosine_schedule, "sigmoid": sigmoid_schedule}
         if noise_schedule not in sched:
@@ -136,7 +134,7 @@ class NaturalSpeech2(nn.Module):
             else:
                 v = self.model.forward_with_cond_scale(audio, times, cond_scale=cond_scale)
             ops.ddim_step(audio, v, alpha.contiguous(), sigma.contiguous(), alpha_next.contiguous(),
-                          sigma_next.contiguous())
+                          sigma_next.contiguous(), objective=self.objective)
         self.model.use_cuda_graphs = graphs_before
         return audio
 
@@ -211,7 +209,7 @@ class NaturalSpeech2(nn.Module):
         alpha, sigma = alpha.contiguous(), sigma.contiguous()
         noised = torch.empty_like(audio)
         target = torch.empty_like(audio)
-        ops.q_sample(audio, noise, alpha, sigma, noised, target)        # ns2.py:1631, 1643-1644
+        ops.q_sample(audio, noise, alpha, sigma, noised, target, objective=self.objective)  # ns2.py:1631-1644
         pred = self.model(noised, times, prompt=prompt_enc, cond=cond)  # ns2.py:1635
         loss = ops.mse_rows(pred, target, torch.empty(batch, device=device))  # ns2.py:1646-1647
         # min-SNR weight on (B,)-sized tensors, with the reference's exact broadcasting (ns2.py:1651-1666):
@@ -221,7 +219,12 @@ class NaturalSpeech2(nn.Module):
         clipped = snr.clone()
         if self.min_snr_loss_weight:
             clipped.clamp_(max=self.min_snr_gamma)
-        loss_weight = clipped / (snr + 1)
+        if self.objective == "eps":       # ns2.py:1657-1664
+            loss_weight = clipped / snr
+        elif self.objective == "x0":
+            loss_weight = clipped
+        else:
+            loss_weight = clipped / (snr + 1)
         return (loss * loss_weight).mean()
 
     p_losses = forward  # the name BASELINE.json's north_star uses; the reference inlines it in forward

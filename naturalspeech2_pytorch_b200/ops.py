@@ -116,8 +116,11 @@ def conv3_segs(k_len: int, tap_stride: Optional[int] = None, acc: int = 0, a_col
 # --------------------------------------------------------------------------------------------------
 # attention
 # --------------------------------------------------------------------------------------------------
+ATTN_AUTO, ATTN_ONE_TILE, ATTN_TWO_TILE, ATTN_TWO_TILE_POLY2, ATTN_TWO_TILE_POLY4 = 0, 1, 2, 3, 4
+
+
 def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tensor, *, heads: int,
-              scale: Optional[float] = None) -> torch.Tensor:
+              scale: Optional[float] = None, kernel: int = ATTN_AUTO) -> torch.Tensor:
     """q: (B, Nq, heads*64), k/v: (B, Nk, heads*64) bf16 (strided views into a fused projection are fine)."""
     lib = _lib.load()
     for name, t in (("q", q), ("k", k), ("v", v), ("out", out)):
@@ -132,6 +135,7 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tens
     args.batches, args.heads = q.shape[0], heads
     args.q_len, args.kv_len, args.dim_head = q.shape[1], k.shape[1], 64
     args.scale = float(scale if scale is not None else 64 ** -0.5)
+    args.kernel = int(kernel)
     check(lib.ns2_attn_fwd(C.byref(args), _stream()), "ns2_attn_fwd")
     return out
 
@@ -246,14 +250,20 @@ def transpose_cast(x: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
 # --------------------------------------------------------------------------------------------------
 # diffusion element-wise
 # --------------------------------------------------------------------------------------------------
-def q_sample(x0, noise, alpha, sigma, x_t, target=None):
+OBJECTIVES = {"v": _lib.NS2_OBJ_V, "eps": _lib.NS2_OBJ_EPS, "x0": _lib.NS2_OBJ_X0}
+
+
+def q_sample(x0, noise, alpha, sigma, x_t, target=None, objective: str = "v"):
+    """x_t = alpha x0 + sigma noise; target of the chosen parameterisation (ns2.py:1631-1644)."""
     lib = _lib.load()
     B = x0.shape[0]
     per = x0.numel() // B
     for name, t in (("x0", x0), ("noise", noise), ("alpha", alpha), ("sigma", sigma), ("x_t", x_t)):
         _req(t, torch.float32, name)
+    if target is not None:
+        _req(target, torch.float32, "target")
     check(lib.ns2_q_sample(x0.data_ptr(), noise.data_ptr(), alpha.data_ptr(), sigma.data_ptr(), B, per,
-                           x_t.data_ptr(), _ptr(target), _stream()), "ns2_q_sample")
+                           x_t.data_ptr(), _ptr(target), OBJECTIVES[objective], _stream()), "ns2_q_sample")
     return x_t, target
 
 
@@ -268,12 +278,14 @@ def mse_rows(pred, target, out, scratch=None):
     return out
 
 
-def ddim_step(x, v, alpha, sigma, alpha_next, sigma_next):
+def ddim_step(x, v, alpha, sigma, alpha_next, sigma_next, objective: str = "v"):
+    """In-place DDIM update of x from the model output `v` (ns2.py:1412-1429)."""
     lib = _lib.load()
     B = x.shape[0]
     per = x.numel() // B
     check(lib.ns2_ddim_step(x.data_ptr(), v.data_ptr(), alpha.data_ptr(), sigma.data_ptr(),
-                            alpha_next.data_ptr(), sigma_next.data_ptr(), B, per, _stream()),
+                            alpha_next.data_ptr(), sigma_next.data_ptr(), B, per, OBJECTIVES[objective],
+                            _stream()),
           "ns2_ddim_step")
     return x
 

@@ -61,19 +61,24 @@ def training_loss(model_fn, x_start, times, noise, objective="v", min_snr_gamma=
     return loss, {"noised": noised, "target": target, "per_sample": per_sample, "weight": w}
 
 
-def ddim_step(x, v, t, t_next, scale=1.0):
-    """One iteration of ddim_sample for objective 'v', ns2.py:1396-1429 (time_difference = 0)."""
+def ddim_step(x, v, t, t_next, scale=1.0, objective="v"):
+    """One iteration of ddim_sample, ns2.py:1396-1429 (time_difference = 0); `v` is the model output."""
     dtype = x.dtype
     g = sigmoid_schedule(np.asarray(t, dtype=dtype))
     gn = sigmoid_schedule(np.asarray(t_next, dtype=dtype))
     a, s = gamma_to_alpha_sigma(g[:, None, None], scale)
     an, sn = gamma_to_alpha_sigma(gn[:, None, None], scale)
-    x0 = a * x - s * v
+    if objective == "v":          # ns2.py:1412-1421
+        x0 = a * x - s * v
+    elif objective == "eps":
+        x0 = (x - s * v) / np.maximum(a, 1e-10)
+    else:
+        x0 = v
     eps = (x - a * x0) / np.maximum(s, 1e-10)
     return x0 * an + eps * sn
 
 
-def ddim_sample(model_fn, x_init, timesteps, scale=1.0):
+def ddim_sample(model_fn, x_init, timesteps, scale=1.0, objective="v"):
     """ddim_sample, ns2.py:1379-1431, from a given initial noise."""
     x = x_init
     B = x.shape[0]
@@ -81,5 +86,5 @@ def ddim_sample(model_fn, x_init, timesteps, scale=1.0):
         tb = np.full((B,), t, dtype=x.dtype)
         tnb = np.full((B,), tn, dtype=x.dtype)
         v = model_fn(x, tb)
-        x = ddim_step(x, v, tb, tnb, scale)
+        x = ddim_step(x, v, tb, tnb, scale, objective)
     return x

@@ -11,12 +11,37 @@ from param_fill import fill_module
 
 GOLDEN = Path(__file__).resolve().parent / "golden"
 MODEL_CASES = ["uncond_small", "cond_small", "cond_samedim", "readme_uncond"]
+# slices of the benchmarked configurations (dim 512, heads 8, seq 1024, depth 2): inputs are regenerated from seeds,
+# outputs are stored on a row subsample (see tests/golden/make_golden.py BIG_CASES)
+BIG_MODEL_CASES = ["cfg2_slice", "cfg3_slice"]
 
 
 def load_model_golden(name: str):
     z = np.load(GOLDEN / f"model_{name}.npz")
     kwargs = dict(ast.literal_eval(str(z["config"])))
     return z, kwargs, int(z["fill_seed"])
+
+
+def golden_inputs(z, kwargs) -> dict:
+    """{x, times[, prompt, cond]} as float32 CPU tensors: stored arrays, or regenerated from the generator's seeds."""
+    from param_fill import seeded, seeded_uniform
+    if "in_seeded" in z.files:
+        shp = tuple(int(v) for v in z["in_shape_x"])
+        out = {"x": seeded(shp, 11), "times": seeded_uniform((shp[0],), 12)}
+        if kwargs.get("condition_on_prompt"):
+            out["prompt"] = seeded(tuple(int(v) for v in z["in_shape_prompt"]), 13)
+            out["cond"] = seeded(tuple(int(v) for v in z["in_shape_cond"]), 14)
+        return out
+    out = {"x": torch.from_numpy(z["in_x"]), "times": torch.from_numpy(z["in_times"])}
+    if kwargs.get("condition_on_prompt"):
+        out["prompt"] = torch.from_numpy(z["in_prompt"])
+        out["cond"] = torch.from_numpy(z["in_cond"])
+    return out
+
+
+def golden_rows(z, out: np.ndarray) -> np.ndarray:
+    """Restrict a full (B, N, D) output to the positions the fixture stores."""
+    return out[:, z["rows"]] if "rows" in z.files else out
 
 
 def build_model(kwargs: dict, seed: int, device="cpu"):

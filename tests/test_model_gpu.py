@@ -12,18 +12,19 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import MODEL_CASES, build_model, err_stats, load_model_golden, numpy_params, oracle_config
+from helpers import (BIG_MODEL_CASES, MODEL_CASES, build_model, err_stats, golden_inputs, golden_rows,
+                     load_model_golden, numpy_params, oracle_config)
 
 pytestmark = pytest.mark.gpu
 
 
 def _run(model, z, kwargs, **fw):
     dev = "cuda"
-    x = torch.from_numpy(z["in_x"]).to(dev)
-    times = torch.from_numpy(z["in_times"]).to(dev)
+    inp = golden_inputs(z, kwargs)
+    x, times = inp["x"].to(dev), inp["times"].to(dev)
     extra = {}
     if kwargs.get("condition_on_prompt"):
-        extra = dict(prompt=torch.from_numpy(z["in_prompt"]).to(dev), cond=torch.from_numpy(z["in_cond"]).to(dev))
+        extra = dict(prompt=inp["prompt"].to(dev), cond=inp["cond"].to(dev))
     return model, x, times, extra
 
 
@@ -45,6 +46,42 @@ def test_model_forward_vs_reference_golden(name):
     np.testing.assert_array_equal(out, out2)
 
 
+@pytest.mark.parametrize("name", BIG_MODEL_CASES)
+def test_model_forward_at_benchmarked_dims(name):
+    """Whole-model parity at the kernel instantiations the bench runs (dim 512, heads 8, seq 1024: 256-wide CTA-pair
+    tiles, n=1408 partial last tile, two-accumulator wavenet tile, 148-SM persistent schedules), chained through the
+    4 wavenet stacks + 2 transformer layers, against the reference's fp64 output.  Same protocol as above; also
+    reports (not asserts — no bf16-operand implementation can meet it, see the module docstring) the fraction of
+    elements inside the north-star rtol=1e-3/atol=1e-5 band against the reference's fp32 output."""
+    z, kwargs, seed = load_model_golden(name)
+    model = build_model(kwargs, seed, device="cuda")
+    model, x, times, extra = _run(model, z, kwargs)
+    full = model(x, times, **extra).float().cpu().numpy()
+    assert np.isfinite(full).all()
+    out = golden_rows(z, full)
+    emax, erms = err_stats(out, z["out_fp64"])
+    ref_max, ref_rms, ref_frac = (float(v) for v in z["stats_out_bf16_autocast"])   # whole-tensor statistics
+    frac = float(np.isclose(out, z["out_fp32"], rtol=1e-3, atol=1e-5).mean())
+    print(f"{name}: ours max={emax:.3e} rms={erms:.3e} strict-band frac vs ref fp32={frac:.4f} | reference "
+          f"bf16-autocast max={ref_max:.3e} rms={ref_rms:.3e} strict-band frac={ref_frac:.4f}")
+    assert emax <= ref_max and erms <= ref_rms, (emax, erms, ref_max, ref_rms)
+    assert emax < 5e-2 and erms < 1e-2, (emax, erms)
+    assert frac >= ref_frac, (frac, ref_frac)
+    if kwargs.get("condition_on_prompt"):
+        null = golden_rows(z, model(x, times, cond_drop_prob=1., **extra).float().cpu().numpy())
+        nmax, nrms = err_stats(null, z["out_fp64_null"])
+        assert nmax < 5e-2 and nrms < 1e-2, (nmax, nrms)
+        cfg = golden_rows(z, model.forward_with_cond_scale(x, times, cond_scale=3., **extra).float().cpu().numpy())
+        cmax, crms = err_stats(cfg, z["out_fp64_cfg3"])
+        # guidance: out = null + 3 (cond - null) amplifies the independent errors of the two passes by <= 3 + 2
+        assert cmax < 5 * 5e-2 and crms < 5 * erms + 1e-3, (cmax, crms)
+    # CUDA-graph replay of the same step is bit-identical
+    model.use_cuda_graphs = True
+    kw = dict(_conditioning=model.precompute_conditioning(extra["prompt"], extra["cond"], x.shape[1])) if extra else {}
+    g = model(x, times, **kw).float().cpu().numpy()
+    np.testing.assert_array_equal(full, g)
+
+
 @pytest.mark.parametrize("name", ["cond_small", "cond_samedim"])
 def test_model_cfg_paths(name):
     z, kwargs, seed = load_model_golden(name)
@@ -55,7 +92,8 @@ def test_model_cfg_paths(name):
     assert emax < 5e-2, emax
     cfg = model.forward_with_cond_scale(x, times, cond_scale=3., **extra).float().cpu().numpy()
     emax, erms = err_stats(cfg, z["out_fp64_cfg3"])
-    assert emax < 2.5e-1 and erms < 5e-2, (emax, erms)  # errors of the two passes are amplified by the scale 3
+    # out = null + 3 (cond - null): the independent errors of the two passes are amplified by at most 3 + 2
+    assert emax < 1.5e-1 and erms < 3e-2, (emax, erms)
 
 
 def test_model_vs_oracle_other_shape():
