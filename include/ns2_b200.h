@@ -116,6 +116,7 @@ typedef struct ns2_attn_args {
 #define NS2_ATTN_TWO_TILE 2        /* persistent, 2 x 128 queries x 128-key tiles, P and O in tensor memory */
 #define NS2_ATTN_TWO_TILE_POLY2 3  /* same, 2 of every 8 exponentials on the FMA pipe (degree-3 polynomial) */
 #define NS2_ATTN_TWO_TILE_POLY4 4  /* same, 4 of every 8 */
+#define NS2_ATTN_TWO_TILE_LOCKSTEP 5 /* two-tile without the exponential-section turn taking (A/B measurement) */
 
 int ns2_attn_fwd(const ns2_attn_args* args, ns2_stream_t stream);
 
@@ -157,6 +158,15 @@ int ns2_cast_bf16(const float* x, const float* add, int64_t count, void* out_bf1
                   ns2_stream_t stream);
 int ns2_mean_rows(const float* x, int32_t batch, int32_t n, int32_t dim, float* out,
                   ns2_stream_t stream);
+/*    ns2_cond_inject      : out_bf16[b,n,:] = bf16(x[b,n,:] + c), c = 0 for n >= cond_len (zero padding, ns2.py:70-77),
+ *                           null_cond[:] where drop_mask[b] (uint8, may be NULL = keep all), else cproj[b,n,:]
+ *                           (cproj: projected aligned condition, token-major (batch, cond_len, dim) f32; ns2.py:978-992)
+ *    ns2_select_rows      : out[b,:] = drop_mask[b] ? null_row[:] : src[b,:]  (f32 or bf16 out; ns2.py:954-968) */
+int ns2_cond_inject(const float* x, const float* cproj, const uint8_t* drop_mask, const float* null_cond,
+                    int32_t batch, int32_t n, int32_t cond_len, int32_t dim, void* out_bf16, ns2_stream_t stream);
+int ns2_select_rows(const uint8_t* drop_mask, const float* null_row, const float* src, int64_t src_row_stride,
+                    int32_t batch, int32_t row_len, void* out, int64_t out_row_stride, int32_t out_bf16,
+                    ns2_stream_t stream);
 int ns2_transpose_cast(const float* x, int32_t batch, int32_t channels, int32_t length,
                        void* out_bf16, ns2_stream_t stream);
 
@@ -166,7 +176,8 @@ int ns2_transpose_cast(const float* x, int32_t batch, int32_t channels, int32_t 
  *    `objective` selects the parameterisation (ns2.py:1637-1644, 1412-1421): NS2_OBJ_V / NS2_OBJ_EPS / NS2_OBJ_X0.
  *    ns2_q_sample   : x_t = alpha*x0 + sigma*noise ; target = alpha*noise - sigma*x0 (v) | noise (eps) | x0 (x0)
  *    ns2_mse_rows   : out[b] = mean((pred-target)^2) over the sample          (ns2.py:1646-1647);
- *                     deterministic two-level reduction through caller-provided scratch
+ *                     deterministic two-level reduction through caller-provided scratch; optionally
+ *                     also the batch mean of those per-sample values (one more tiny launch)
  *    ns2_ddim_step  : x0 = alpha*x - sigma*out (v) | (x - sigma*out)/max(alpha,1e-10) (eps) | out (x0) ;
  *                     eps = (x - alpha*x0)/max(sigma,1e-10) ;
  *                     x <- x0*alpha_next + eps*sigma_next                     (ns2.py:1420-1429)
@@ -181,12 +192,17 @@ int ns2_q_sample(const float* x0, const float* noise, const float* alpha, const 
                  ns2_stream_t stream);
 int ns2_mse_rows(const float* pred, const float* target, int32_t batch, int64_t per_sample,
                  float* scratch /* batch * NS2_MSE_SCRATCH_PER_SAMPLE floats */, float* out,
+                 float* mean_out /* optional: mean over the batch of out[], ns2.py:1666 */,
                  ns2_stream_t stream);
 int ns2_ddim_step(float* x, const float* v, const float* alpha, const float* sigma,
                   const float* alpha_next, const float* sigma_next, int32_t batch,
                   int64_t per_sample, int32_t objective, ns2_stream_t stream);
 int ns2_cfg_combine(const float* cond, const float* null_, float scale, int64_t count, float* out,
                     ns2_stream_t stream);
+/*    ns2_x_start    : x_start implied by the model output `pred` (ns2.py:1673-1680): alpha*x - sigma*pred (v) |
+ *                     (x - sigma*pred)/max(alpha,1e-10) (eps) | pred (x0) */
+int ns2_x_start(const float* x, const float* pred, const float* alpha, const float* sigma, int32_t batch,
+                int64_t per_sample, float* out, int32_t objective, ns2_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * 7. Residual vector quantisation (Encodec RVQ encode/decode; third-party code reached from
@@ -198,15 +214,25 @@ int ns2_cfg_combine(const float* cond, const float* null_, float scale, int64_t 
  *                      K a multiple of 128.
  *    ns2_rvq_decode  : emb f32 (F, d) = sum_q codebooks[q, codes[f,q], :]  (summed in order q = 0..Q-1)
  * ------------------------------------------------------------------------------------------------ */
+#define NS2_RVQ_STATS_LEN 4
 int ns2_rvq_prepare(const float* codebooks, int32_t q, int32_t k, int32_t d, void* cb_f16,
                     float* cb_norm2, float* cb_meta, ns2_stream_t stream);
 int ns2_rvq_encode(const float* frames, int64_t num_frames, int32_t d, const float* codebooks,
                    const void* cb_f16, const float* cb_norm2, const float* cb_meta, int32_t q,
                    int32_t k, int64_t* codes,
-                   int64_t* stats /* optional 3 counters {lookups, near-ties re-scored, full scans} */,
+                   int64_t* stats /* optional NS2_RVQ_STATS_LEN int64 counters, accumulated with atomics:
+                                     {lookups, near-ties re-scored, full scans, sub-chunk scans} */,
                    ns2_stream_t stream);
 int ns2_rvq_decode(const int64_t* codes, int64_t num_frames, int32_t q, int32_t k, int32_t d,
                    const float* codebooks, float* emb, ns2_stream_t stream);
+/*    ns2_rvq_ce      : cross-entropy head of the residual VQ, `codec.rq(x_start, codes)` (ns2.py:1670-1684;
+ *                      vector-quantize-pytorch ResidualVQ.forward(x, indices)).  Per stage the logits are the negative
+ *                      Euclidean distances -||r_q - c_k||; loss = sum_q mean_{f: target != -1} CE(logits, target[f,q]);
+ *                      the residual chain follows `own_codes` (the codec's own nearest codewords, from ns2_rvq_encode).
+ *                      ce_scratch: num_frames * q floats; loss: 1 float. */
+int ns2_rvq_ce(const float* frames, int64_t num_frames, int32_t d, const float* codebooks,
+               const float* cb_norm2, int32_t q, int32_t k, const int64_t* own_codes,
+               const int64_t* target_codes, float* ce_scratch, float* loss, ns2_stream_t stream);
 
 /* Number of kernel launches issued through this library since load (for bench.py's gpu_launches). */
 int64_t ns2_launch_count(void);

@@ -14,6 +14,7 @@ NS2_EPI_BF16, NS2_EPI_F32, NS2_EPI_GEGLU, NS2_EPI_WAVENET = 0, 1, 2, 3
 NS2_GEMM_MAX_SEGS = 8
 NS2_GEMM_MAX_GROUPS = 8
 NS2_MSE_SCRATCH_PER_SAMPLE = 64
+NS2_RVQ_STATS_LEN = 4
 NS2_OBJ_V, NS2_OBJ_EPS, NS2_OBJ_X0 = 0, 1, 2
 NS2_ABI_VERSION = 2
 
@@ -66,13 +67,17 @@ SIGNATURES = {
     "ns2_cast_bf16": (C.c_int, [_P, _P, _I64, _P, _P]),
     "ns2_mean_rows": (C.c_int, [_P, _I32, _I32, _I32, _P, _P]),
     "ns2_transpose_cast": (C.c_int, [_P, _I32, _I32, _I32, _P, _P]),
+    "ns2_cond_inject": (C.c_int, [_P, _P, _P, _P, _I32, _I32, _I32, _I32, _P, _P]),
+    "ns2_select_rows": (C.c_int, [_P, _P, _P, _I64, _I32, _I32, _P, _I64, _I32, _P]),
     "ns2_q_sample": (C.c_int, [_P, _P, _P, _P, _I32, _I64, _P, _P, _I32, _P]),
-    "ns2_mse_rows": (C.c_int, [_P, _P, _I32, _I64, _P, _P, _P]),
+    "ns2_mse_rows": (C.c_int, [_P, _P, _I32, _I64, _P, _P, _P, _P]),
     "ns2_ddim_step": (C.c_int, [_P, _P, _P, _P, _P, _P, _I32, _I64, _I32, _P]),
     "ns2_cfg_combine": (C.c_int, [_P, _P, _F, _I64, _P, _P]),
+    "ns2_x_start": (C.c_int, [_P, _P, _P, _P, _I32, _I64, _P, _I32, _P]),
     "ns2_rvq_prepare": (C.c_int, [_P, _I32, _I32, _I32, _P, _P, _P, _P]),
     "ns2_rvq_encode": (C.c_int, [_P, _I64, _I32, _P, _P, _P, _P, _I32, _I32, _P, _P, _P]),
     "ns2_rvq_decode": (C.c_int, [_P, _I64, _I32, _I32, _I32, _P, _P, _P]),
+    "ns2_rvq_ce": (C.c_int, [_P, _I64, _I32, _P, _P, _I32, _I32, _P, _P, _P, _P, _P]),
 }
 
 _lib = None

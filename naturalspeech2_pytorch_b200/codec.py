@@ -85,5 +85,17 @@ class EncodecRVQ(nn.Module):
             return emb
         return self.decoder(emb)
 
-    def rq(self, *args, **kwargs):
-        raise NotImplementedError("codec.rq (RVQ cross-entropy head, SURVEY a17) is optional and not built")
+    @torch.no_grad()
+    def rq(self, x: torch.Tensor, codes: torch.Tensor):
+        """The call `NaturalSpeech2.forward` makes when rvq_cross_entropy_loss_weight != 0 (ns2.py:1682):
+        `_, ce_loss = codec.rq(x_start, codes)` — vector-quantize-pytorch's ResidualVQ.forward(x, indices=codes).
+        Per stage: logits = -||r_q - c_k|| (Euclidean), cross-entropy against codes[..., q] (ignore_index -1),
+        residual chain through the codec's own nearest codewords; returns (quantized, summed CE loss)."""
+        shp = x.shape[:-1]
+        flat = x.reshape(-1, 128).float().contiguous()
+        tgt = codes.reshape(-1, self.num_quantizers).to(torch.int64).contiguous()
+        prep = self._prep()
+        own = ops.rvq_encode(flat, self.codebooks, prep)
+        loss = ops.rvq_ce(flat, self.codebooks, prep[1], own, tgt)
+        emb = ops.rvq_decode(own, self.codebooks)
+        return emb.view(*shp, 128), loss

@@ -397,7 +397,10 @@ __device__ __forceinline__ void exp2_poly_x2(unsigned long long x, float& y0, fl
 }
 
 // POLY: how many of every 8 consecutive exponentials are evaluated on the FMA pipe instead of MUFU (0, 2 or 4)
-template <int POLY>
+// STAGGER: the two warps that share an SM sub-partition (same TMEM lane quarter, one per warpgroup) take turns in the
+//          exponential section, so that one warp's MUFU-bound phase overlaps the other's load / max / store phases
+//          instead of both fighting for the MUFU at the same time and then both leaving it idle
+template <int POLY, bool STAGGER>
 __global__ void __launch_bounds__(attn2::THREADS, 1) attn2_fwd_kernel(const __grid_constant__ Attn2Dev p) {
   using namespace attn2;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -410,7 +413,8 @@ __global__ void __launch_bounds__(attn2::THREADS, 1) attn2_fwd_kernel(const __gr
   uint64_t* s_free = bars + 6 + 2 * KVS;    // [2] softmax -> MMA: S^w is in registers (4 warp arrivals)
   uint64_t* p_full = bars + 8 + 2 * KVS;    // [2] softmax -> MMA: P^w is in TMEM (4 warp arrivals)
   uint64_t* o_full = bars + 10 + 2 * KVS;   // [2] MMA -> softmax: O^w += P^w V complete
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 12 + 2 * KVS);
+  uint64_t* turn = bars + 12 + 2 * KVS;     // [2][4] warp (w, quarter) has finished its exponential section
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 20 + 2 * KVS);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int T = (p.kv_len + BKV - 1) / BKV;
@@ -439,6 +443,7 @@ __global__ void __launch_bounds__(attn2::THREADS, 1) attn2_fwd_kernel(const __gr
       mbar_init(smem_u32(&kv_full[i]), 1);
       mbar_init(smem_u32(&kv_empty[i]), 1);
     }
+    for (int i = 0; i < 8; ++i) mbar_init(smem_u32(&turn[i]), 1);
     fence_barrier_init();
   }
   if (warp == 8) tmem_alloc(smem_u32(tmem_holder), 512);
@@ -618,6 +623,19 @@ __global__ void __launch_bounds__(attn2::THREADS, 1) attn2_fwd_kernel(const __gr
           m_run = m_tile;
           l_run = 0.f;
         }
+        if constexpr (STAGGER) {
+          // strict alternation per lane quarter: warpgroup 0's tile g, warpgroup 1's tile g, warpgroup 0's tile g+1 ...
+          if (w == 0) {
+            if (g > 0) mbar_wait(smem_u32(&turn[4 + qw]), (g - 1) & 1);
+          } else {
+            mbar_wait(smem_u32(&turn[qw]), g & 1);
+          }
+        }
+        // the P buffer is read by the previous tile's P.V until o_full flips (long done by now)
+        if (j > 0) {
+          mbar_wait(smem_u32(&o_full[w]), (g - 1) & 1);
+          tc_fence_after();
+        }
         // P = exp2(s*c - m) -> bf16 pairs; row sum in fp32
         const unsigned long long nm2 = pack_f32x2(-m_run, -m_run);
         unsigned long long lsum0 = 0ull, lsum1 = 0ull;  // two packed (0.f, 0.f) accumulators
@@ -650,6 +668,11 @@ __global__ void __launch_bounds__(attn2::THREADS, 1) attn2_fwd_kernel(const __gr
             if (i < BKV / 2) pk_lo[i / 2 + q] = v;
             else pk_hi[(i - BKV / 2) / 2 + q] = v;
           }
+          if (i == BKV / 2 - 8) tmem_st32(p_addr, pk_lo);   // first half of P goes out while the second is computed
+        }
+        if constexpr (STAGGER) {
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&turn[w * 4 + qw]));
         }
         {
           float a0, a1, b0, b1;
@@ -657,12 +680,6 @@ __global__ void __launch_bounds__(attn2::THREADS, 1) attn2_fwd_kernel(const __gr
           unpack_f32x2(lsum1, b0, b1);
           l_run += (a0 + a1) + (b0 + b1);
         }
-        // the P buffer is still being read by the previous tile's P.V until o_full flips
-        if (j > 0) {
-          mbar_wait(smem_u32(&o_full[w]), (g - 1) & 1);
-          tc_fence_after();
-        }
-        tmem_st32(p_addr, pk_lo);
         tmem_st32(p_addr + 32, pk_hi);
         tmem_st_wait();
         tc_fence_before();
@@ -754,8 +771,7 @@ extern "C" int ns2_attn_fwd(const ns2_attn_args* a, ns2_stream_t stream_) {
   // perceiver latents) and short query sequences (the perceiver itself).  args->kernel overrides (tests, tuning).
   int kernel = a->kernel;
   if (kernel == NS2_ATTN_AUTO) kernel = (a->kv_len > 64 && a->q_len > 128) ? NS2_ATTN_TWO_TILE : NS2_ATTN_ONE_TILE;
-  NS2_REQUIRE(kernel == NS2_ATTN_ONE_TILE || kernel == NS2_ATTN_TWO_TILE || kernel == NS2_ATTN_TWO_TILE_POLY2 ||
-                  kernel == NS2_ATTN_TWO_TILE_POLY4,
+  NS2_REQUIRE(kernel >= NS2_ATTN_ONE_TILE && kernel <= NS2_ATTN_TWO_TILE_LOCKSTEP,
               "attn_fwd: unknown kernel selector %d", a->kernel);
   if (kernel == NS2_ATTN_ONE_TILE) {
     NS2_CUDA_CHECK(set_max_smem_once(attn_fwd_kernel, attn::SMEM_BYTES));
@@ -791,16 +807,19 @@ extern "C" int ns2_attn_fwd(const ns2_attn_args* a, ns2_stream_t stream_) {
   d2.num_items = d2.q_pairs * a->heads * a->batches;
   d2.scale_log2e = a->scale * 1.4426950408889634f;
   const int grid2 = d2.num_items < num_sms() ? d2.num_items : num_sms();
-  if (kernel == NS2_ATTN_TWO_TILE) {
-    NS2_CUDA_CHECK(set_max_smem_once(attn2_fwd_kernel<0>, attn2::SMEM_BYTES));
-    attn2_fwd_kernel<0><<<grid2, attn2::THREADS, attn2::SMEM_BYTES, stream>>>(d2);
-  } else if (kernel == NS2_ATTN_TWO_TILE_POLY2) {
-    NS2_CUDA_CHECK(set_max_smem_once(attn2_fwd_kernel<2>, attn2::SMEM_BYTES));
-    attn2_fwd_kernel<2><<<grid2, attn2::THREADS, attn2::SMEM_BYTES, stream>>>(d2);
-  } else {
-    NS2_CUDA_CHECK(set_max_smem_once(attn2_fwd_kernel<4>, attn2::SMEM_BYTES));
-    attn2_fwd_kernel<4><<<grid2, attn2::THREADS, attn2::SMEM_BYTES, stream>>>(d2);
+  auto launch2 = [&](auto kern) -> int {
+    NS2_CUDA_CHECK(set_max_smem_once(kern, attn2::SMEM_BYTES));
+    kern<<<grid2, attn2::THREADS, attn2::SMEM_BYTES, stream>>>(d2);
+    return kOk;
+  };
+  int rc2;
+  switch (kernel) {
+    case NS2_ATTN_TWO_TILE: rc2 = launch2(attn2_fwd_kernel<0, true>); break;
+    case NS2_ATTN_TWO_TILE_POLY2: rc2 = launch2(attn2_fwd_kernel<2, true>); break;
+    case NS2_ATTN_TWO_TILE_POLY4: rc2 = launch2(attn2_fwd_kernel<4, true>); break;
+    default: rc2 = launch2(attn2_fwd_kernel<0, false>); break;
   }
+  if (rc2 != kOk) return rc2;
   g_launches.fetch_add(1, std::memory_order_relaxed);
   NS2_CUDA_CHECK(cudaGetLastError());
   return kOk;

@@ -170,6 +170,42 @@ __global__ void __launch_bounds__(256) cast_bf16_kernel(const float4* __restrict
   }
 }
 
+// out[b, n, :] = bf16(x[b, n, :] + c) with c = 0 for n >= L (zero padding of pad_or_curtail_to_length, ns2.py:70-77),
+// null_cond[:] for a dropped sample, else cproj[b, n, :]   (torch.where(cond_drop_mask, null_cond, cond) + x, ns2.py:982-992)
+__global__ void __launch_bounds__(256) cond_inject_kernel(const float4* __restrict__ x, const float4* __restrict__ cproj,
+                                                          const uint8_t* __restrict__ drop, const float4* __restrict__ null4,
+                                                          int n, int L, int d4, uint2* __restrict__ out) {
+  const int b = blockIdx.y;
+  const bool dropped = drop != nullptr && drop[b] != 0;
+  const long long per = static_cast<long long>(n) * d4;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < per;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int pos = static_cast<int>(i / d4), c = static_cast<int>(i - static_cast<long long>(pos) * d4);
+    float4 v = __ldg(x + b * per + i);
+    if (pos < L) {
+      const float4 a = dropped ? __ldg(null4 + c) : __ldg(cproj + (static_cast<long long>(b) * L + pos) * d4 + c);
+      v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
+    }
+    uint2 w;
+    w.x = pack_bf16x2(v.x, v.y);
+    w.y = pack_bf16x2(v.z, v.w);
+    out[b * per + i] = w;
+  }
+}
+
+// out[b, :] = drop[b] ? null_row[:] : src[b, :]   (fp32 or bf16 output; torch.where of ns2.py:954-968)
+__global__ void __launch_bounds__(256) select_rows_kernel(const uint8_t* __restrict__ drop, const float* __restrict__ null_row,
+                                                          const float* __restrict__ src, long long src_rs, int row_len,
+                                                          void* __restrict__ out, long long out_rs, int out_bf16) {
+  const int b = blockIdx.y;
+  const bool dropped = drop[b] != 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < row_len; i += gridDim.x * blockDim.x) {
+    const float v = dropped ? __ldg(null_row + i) : __ldg(src + b * src_rs + i);
+    if (out_bf16) reinterpret_cast<__nv_bfloat16*>(out)[b * out_rs + i] = __float2bfloat16_rn(v);
+    else reinterpret_cast<float*>(out)[b * out_rs + i] = v;
+  }
+}
+
 __global__ void __launch_bounds__(256) mean_rows_kernel(const float* __restrict__ x, int n, int dim,
                                                         float* __restrict__ out) {
   const int b = blockIdx.y;
@@ -262,6 +298,21 @@ __global__ void mse_final_kernel(const float* __restrict__ partial, long long pe
   if (threadIdx.x == 0) out[b] = (red[0] + red[1]) / static_cast<float>(per_sample);
 }
 
+// mean of `n` per-sample values (one block; fixed summation order => deterministic)
+__global__ void __launch_bounds__(256) batch_mean_kernel(const float* __restrict__ v, int n, float* __restrict__ out) {
+  float s = 0.f;
+  for (int i = threadIdx.x; i < n; i += 256) s += v[i];
+  __shared__ float red[8];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float t = threadIdx.x < 8 ? red[threadIdx.x] : 0.f;
+    t = warp_sum(t);
+    if (threadIdx.x == 0) out[0] = t / static_cast<float>(n);
+  }
+}
+
 __global__ void __launch_bounds__(256) ddim_step_kernel(float4* __restrict__ x,
                                                         const float4* __restrict__ v,
                                                         const float* __restrict__ alpha,
@@ -285,6 +336,24 @@ __global__ void __launch_bounds__(256) ddim_step_kernel(float4* __restrict__ x,
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const float4 xv = x[base + i], vv = __ldg(v + base + i);
     x[base + i] = make_float4(upd(xv.x, vv.x), upd(xv.y, vv.y), upd(xv.z, vv.z), upd(xv.w, vv.w));
+  }
+}
+
+// x_start implied by a model output under the chosen parameterisation (ns2.py:1673-1680)
+__global__ void __launch_bounds__(256) x_start_kernel(const float4* __restrict__ x, const float4* __restrict__ pred,
+                                                      const float* __restrict__ alpha, const float* __restrict__ sigma,
+                                                      long long per4, float4* __restrict__ out, int objective) {
+  const int b = blockIdx.y;
+  const float a = alpha[b], s = sigma[b];
+  const float a_safe = fmaxf(a, 1e-10f);
+  const long long base = static_cast<long long>(b) * per4;
+  auto f = [&](float xv, float pv) {
+    return objective == NS2_OBJ_V ? a * xv - s * pv : (objective == NS2_OBJ_EPS ? (xv - s * pv) / a_safe : pv);
+  };
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < per4;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float4 xv = __ldg(x + base + i), pv = __ldg(pred + base + i);
+    out[base + i] = make_float4(f(xv.x, pv.x), f(xv.y, pv.y), f(xv.z, pv.z), f(xv.w, pv.w));
   }
 }
 
@@ -376,6 +445,35 @@ int ns2_cast_bf16(const float* x, const float* add, int64_t count, void* out_bf1
   return kOk;
 }
 
+int ns2_cond_inject(const float* x, const float* cproj, const uint8_t* drop_mask, const float* null_cond,
+                    int32_t batch, int32_t n, int32_t cond_len, int32_t dim, void* out_bf16, ns2_stream_t stream) {
+  NS2_REQUIRE(x && cproj && out_bf16 && batch > 0 && n > 0 && cond_len > 0 && dim > 0 && dim % 4 == 0,
+              "cond_inject: bad arguments");
+  NS2_REQUIRE(drop_mask == nullptr || null_cond != nullptr, "cond_inject: a drop mask needs null_cond");
+  NS2_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(cproj) |
+                reinterpret_cast<uintptr_t>(null_cond)) & 15) == 0, "cond_inject: pointers must be 16-byte aligned");
+  const long long per4 = static_cast<long long>(n) * (dim / 4);
+  dim3 grid(static_cast<unsigned>((per4 + 255) / 256 > 512 ? 512 : (per4 + 255) / 256), batch);
+  cond_inject_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const float4*>(x), reinterpret_cast<const float4*>(cproj), drop_mask,
+      reinterpret_cast<const float4*>(null_cond), n, cond_len, dim / 4, reinterpret_cast<uint2*>(out_bf16));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  NS2_CUDA_CHECK(cudaGetLastError());
+  return kOk;
+}
+
+int ns2_select_rows(const uint8_t* drop_mask, const float* null_row, const float* src, int64_t src_row_stride,
+                    int32_t batch, int32_t row_len, void* out, int64_t out_row_stride, int32_t out_bf16,
+                    ns2_stream_t stream) {
+  NS2_REQUIRE(drop_mask && null_row && src && out && batch > 0 && row_len > 0, "select_rows: bad arguments");
+  dim3 grid((row_len + 255) / 256 > 64 ? 64 : (row_len + 255) / 256, batch);
+  select_rows_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(drop_mask, null_row, src, src_row_stride,
+                                                                          row_len, out, out_row_stride, out_bf16);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  NS2_CUDA_CHECK(cudaGetLastError());
+  return kOk;
+}
+
 int ns2_mean_rows(const float* x, int32_t batch, int32_t n, int32_t dim, float* out,
                   ns2_stream_t stream) {
   NS2_REQUIRE(x && out && batch > 0 && n > 0 && dim > 0, "mean_rows: bad arguments");
@@ -413,7 +511,7 @@ int ns2_q_sample(const float* x0, const float* noise, const float* alpha, const 
 }
 
 int ns2_mse_rows(const float* pred, const float* target, int32_t batch, int64_t per_sample,
-                 float* partial, float* out, ns2_stream_t stream) {
+                 float* partial, float* out, float* mean_out, ns2_stream_t stream) {
   NS2_REQUIRE(pred && target && out && partial, "mse_rows: NULL pointer");
   NS2_REQUIRE(per_sample % 4 == 0 && batch > 0, "mse_rows: bad sizes");
   dim3 grid(kMseBlocks, batch);
@@ -422,6 +520,10 @@ int ns2_mse_rows(const float* pred, const float* target, int32_t batch, int64_t 
       partial);
   mse_final_kernel<<<batch, 64, 0, static_cast<cudaStream_t>(stream)>>>(partial, per_sample, out);
   g_launches.fetch_add(2, std::memory_order_relaxed);
+  if (mean_out != nullptr) {
+    batch_mean_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(out, batch, mean_out);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+  }
   NS2_CUDA_CHECK(cudaGetLastError());
   return kOk;
 }
@@ -436,6 +538,20 @@ int ns2_ddim_step(float* x, const float* v, const float* alpha, const float* sig
   ddim_step_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<float4*>(x), reinterpret_cast<const float4*>(v), alpha, sigma, alpha_next,
       sigma_next, per_sample / 4, objective);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  NS2_CUDA_CHECK(cudaGetLastError());
+  return kOk;
+}
+
+int ns2_x_start(const float* x, const float* pred, const float* alpha, const float* sigma, int32_t batch,
+                int64_t per_sample, float* out, int32_t objective, ns2_stream_t stream) {
+  NS2_REQUIRE(x && pred && alpha && sigma && out, "x_start: NULL pointer");
+  NS2_REQUIRE(per_sample % 4 == 0 && batch > 0, "x_start: per_sample must be a multiple of 4");
+  NS2_REQUIRE(objective >= NS2_OBJ_V && objective <= NS2_OBJ_X0, "x_start: unknown objective %d", objective);
+  dim3 grid(grid_for(per_sample / 4) / (batch > 8 ? 4 : 1) + 1, batch);
+  x_start_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const float4*>(x), reinterpret_cast<const float4*>(pred), alpha, sigma, per_sample / 4,
+      reinterpret_cast<float4*>(out), objective);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   NS2_CUDA_CHECK(cudaGetLastError());
   return kOk;

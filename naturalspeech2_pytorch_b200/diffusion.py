@@ -13,6 +13,7 @@ give a `conditioner` callable that produces them (e.g. the reference modules, se
 from __future__ import annotations
 
 import math
+from collections import OrderedDict
 from functools import partial
 from typing import Callable, Optional
 
@@ -88,10 +89,9 @@ class NaturalSpeech2(nn.Module):
         self.min_snr_loss_weight = min_snr_loss_weight
         self.min_snr_gamma = min_snr_gamma
         self.rvq_cross_entropy_loss_weight = rvq_cross_entropy_loss_weight
-        if rvq_cross_entropy_loss_weight != 0:
-            raise NotImplementedError("codec.rq cross-entropy head (SURVEY a17) is optional and not built")
         self.conditioner = conditioner
-        self.cuda_graphs = cuda_graphs  # sampling loop: replay one captured CUDA graph per denoiser step
+        self.cuda_graphs = cuda_graphs  # sampling loop: replay one captured CUDA graph per sampling step
+        self._sampler_graphs = OrderedDict()
         self.conditioning_kwargs = conditioning_kwargs  # accepted for signature parity (encoder hyper-parameters)
 
     @property
@@ -108,34 +108,96 @@ class NaturalSpeech2(nn.Module):
     # ------------------------------------------------------------------------------------------
     # sampling
     # ------------------------------------------------------------------------------------------
+    def _schedule_tables(self, batch, device):
+        """(times (T, B), coef (T, 4, B) = alpha, sigma, alpha_next, sigma_next) for every sampling step, computed with
+        the reference's own element-wise formulas (ns2.py:1303-1308, 1396-1404), so the values are bit-identical to
+        the per-step tensors the reference builds."""
+        t_all = torch.linspace(1., 0., self.timesteps + 1, device=device)
+        gamma = self.gamma_schedule(t_all)
+        alpha, sigma = gamma_to_alpha_sigma(gamma, self.scale)
+        coef = torch.stack((alpha[:-1], sigma[:-1], alpha[1:], sigma[1:]), dim=1)      # (T, 4)
+        times = t_all[:-1, None].expand(-1, batch).contiguous()
+        return times, coef[:, :, None].expand(-1, -1, batch).contiguous()
+
+    def _sampler_entry(self, shape, conditioning, cond_scale, device):
+        """One captured CUDA graph = one whole sampling step: denoiser forward(s), guidance combine, DDIM update of the
+        static latent buffer.  Keyed on shapes only; conditioning is copied into static buffers."""
+        guided = self.conditional and cond_scale != 1.
+        cond_sig = None
+        if conditioning is not None:
+            cond_sig = tuple(tuple(v.shape) for v in conditioning.values() if torch.is_tensor(v))
+        key = (tuple(shape), cond_sig, float(cond_scale) if guided else None, self.objective, str(device))
+        entry = self._sampler_graphs.get(key)
+        if entry is not None and entry["packed"] is self.model.packed():
+            self._sampler_graphs.move_to_end(key)
+            if conditioning is not None:
+                for k, v in conditioning.items():
+                    if torch.is_tensor(v):
+                        entry["cond"][k].copy_(v)
+            return entry
+        while len(self._sampler_graphs) >= 4:
+            self._sampler_graphs.popitem(last=False)
+        B = shape[0]
+        model = self.model
+        x = torch.empty(shape, device=device, dtype=torch.float32)
+        ts = torch.zeros(B, device=device, dtype=torch.float32)
+        coef = torch.ones(4, B, device=device, dtype=torch.float32)
+        v0 = torch.empty_like(x)
+        v1 = torch.empty_like(x) if guided else None
+        static_cond = None
+        if conditioning is not None:
+            static_cond = type(conditioning)({k: (v.clone() if torch.is_tensor(v) else v)
+                                              for k, v in conditioning.items()})
+        p_cond = 0. if self.conditional else None
+
+        def step():
+            model._forward_impl(x, ts, None, None, None, p_cond, static_cond, v0)
+            if guided:   # classifier-free guidance (ns2.py:914-927): conditional + null forward, lerp
+                model._forward_impl(x, ts, None, None, None, 1., static_cond, v1)
+                ops.cfg_combine(v0, v1, cond_scale, v0)
+            ops.ddim_step(x, v0, coef[0], coef[1], coef[2], coef[3], objective=self.objective)
+
+        x.normal_()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):   # warm-up outside capture (workspaces, packing)
+            step()
+        torch.cuda.current_stream().wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, capture_error_mode="thread_local"):
+            step()
+        entry = {"graph": graph, "x": x, "ts": ts, "coef": coef, "cond": static_cond, "packed": model.packed()}
+        self._sampler_graphs[key] = entry
+        return entry
+
     @torch.no_grad()
     def ddim_sample(self, shape, prompt=None, time_difference=None, cond_scale=1., cond=None, *, noise=None):
-        """ns2.py:1379-1431.  `noise` (optional) fixes the initial latent instead of drawing it."""
+        """ns2.py:1379-1431.  `noise` (optional) fixes the initial latent instead of drawing it.
+        (`time_difference` only shifts a value the reference never reads again, ns2.py:1404-1406.)"""
         batch, device = shape[0], self.device
-        time_difference = self.time_difference if time_difference is None else time_difference
-        time_pairs = self.get_sampling_timesteps(batch, device=device)
         audio = torch.randn(shape, device=device) if noise is None else noise.to(device).float().clone()
         conditioning = None
         if self.conditional:
             assert _exists(prompt) and _exists(cond)
             # timestep-invariant work (perceiver, prompt FiLM vector, aligned-condition projection) once
             conditioning = self.model.precompute_conditioning(prompt, cond, shape[1])
-        graphs_before = self.model.use_cuda_graphs
-        self.model.use_cuda_graphs = graphs_before or self.cuda_graphs
-        for times, times_next in time_pairs:
-            gamma = self.gamma_schedule(times)
-            gamma_next = self.gamma_schedule(times_next)
-            alpha, sigma = gamma_to_alpha_sigma(gamma, self.scale)
-            alpha_next, sigma_next = gamma_to_alpha_sigma(gamma_next, self.scale)
-            times_next = (times_next - time_difference).clamp(min=0.)
+        times_tab, coef_tab = self._schedule_tables(batch, device)
+        if self.cuda_graphs and audio.is_cuda and self.model._prof is None:
+            entry = self._sampler_entry(shape, conditioning, cond_scale, device)
+            entry["x"].copy_(audio)
+            for i in range(self.timesteps):
+                entry["ts"].copy_(times_tab[i])
+                entry["coef"].copy_(coef_tab[i])
+                entry["graph"].replay()
+            return entry["x"].clone()
+        for i in range(self.timesteps):
             if self.conditional:
-                v = self.model.forward_with_cond_scale(audio, times, cond_scale=cond_scale,
+                v = self.model.forward_with_cond_scale(audio, times_tab[i], cond_scale=cond_scale,
                                                        _conditioning=conditioning)
             else:
-                v = self.model.forward_with_cond_scale(audio, times, cond_scale=cond_scale)
-            ops.ddim_step(audio, v, alpha.contiguous(), sigma.contiguous(), alpha_next.contiguous(),
-                          sigma_next.contiguous(), objective=self.objective)
-        self.model.use_cuda_graphs = graphs_before
+                v = self.model.forward_with_cond_scale(audio, times_tab[i], cond_scale=cond_scale)
+            c = coef_tab[i]
+            ops.ddim_step(audio, v, c[0], c[1], c[2], c[3], objective=self.objective)
         return audio
 
     def process_prompt(self, prompt=None):
@@ -225,6 +287,13 @@ class NaturalSpeech2(nn.Module):
             loss_weight = clipped
         else:
             loss_weight = clipped / (snr + 1)
-        return (loss * loss_weight).mean()
+        loss = (loss * loss_weight).mean()
+        if self.rvq_cross_entropy_loss_weight == 0 or not _exists(codes):   # ns2.py:1670-1671
+            return loss
+        # cross entropy of the predicted x_start against the codec's codes (ns2.py:1673-1684)
+        x_start = torch.empty_like(audio)
+        ops.x_start_from_pred(audio, pred, alpha, sigma, x_start, objective=self.objective)
+        _, ce_loss = self.codec.rq(x_start, codes)
+        return loss + self.rvq_cross_entropy_loss_weight * ce_loss
 
     p_losses = forward  # the name BASELINE.json's north_star uses; the reference inlines it in forward

@@ -18,6 +18,8 @@ fp32 output (the protocol of SURVEY section 7, H1).
 from __future__ import annotations
 
 import math
+import weakref
+from collections import OrderedDict
 from typing import Dict, Optional
 
 import torch
@@ -137,6 +139,11 @@ class _PerceiverParams(nn.Module):
         self.norm = _RMSNormParams(dim)
 
 
+class Conditioning(dict):
+    """Timestep-invariant conditioning of one (prompt, cond) pair (`Model.precompute_conditioning`): a dict subclass so
+    that captured CUDA graphs can remember — through a weak reference — which conditioning their static buffers hold."""
+
+
 def _prob_mask_like(shape, prob, device):
     # ns2.py:79-85 — kept in torch so the RNG stream matches the reference (SURVEY H7)
     if prob == 1:
@@ -202,11 +209,13 @@ class Model(nn.Module):
                                               cross_attn=condition_on_prompt)
         self._packed: Optional[Dict[str, torch.Tensor]] = None
         self._packed_sig = None
-        self._ws: Dict[tuple, Dict[str, torch.Tensor]] = {}
+        self._ws: "OrderedDict[tuple, Dict[str, torch.Tensor]]" = OrderedDict()
         self.freeze_packed = False  # set True to skip the per-call parameter-version check (inference loops)
         self._prof = None           # bench.py: list collecting (op name, start event, end event)
         self.use_cuda_graphs = False  # replay one captured CUDA graph per problem shape instead of ~110 launches
-        self._graphs: Dict[tuple, tuple] = {}
+        self._graphs: "OrderedDict[tuple, dict]" = OrderedDict()
+        self.max_cached_shapes = 4  # LRU bound on per-(B, N) workspaces (~1.3 GB each at cfg2) and captured graphs
+        self.register_load_state_dict_post_hook(lambda module, incompatible: module.invalidate_packed())
 
     @property
     def device(self):
@@ -217,6 +226,22 @@ class Model(nn.Module):
     # ----------------------------------------------------------------------------------------------
     def _signature(self):
         return tuple((p.data_ptr(), p._version) for p in self.parameters())
+
+    def invalidate_packed(self) -> None:
+        """Drop the packed bf16 weights and every captured CUDA graph (they hold pointers into the packed copies).
+        Called automatically by `load_state_dict`, `.to()` / `.cuda()` / `.float()` and whenever a parameter's
+        version counter moves (optimizer steps, in-place ops).  Updates made THROUGH `.data` (e.g. the
+        `p.data.lerp_()` of ema_pytorch) do not bump the version counter: call this after them."""
+        self._packed = None
+        self._packed_sig = None
+        self._graphs.clear()
+
+    def _apply(self, fn, *args, **kwargs):
+        out = super()._apply(fn, *args, **kwargs)
+        if hasattr(self, "_graphs"):
+            self.invalidate_packed()
+            self._ws.clear()
+        return out
 
     def packed(self) -> Dict[str, torch.Tensor]:
         if self._packed is not None and self.freeze_packed:
@@ -342,7 +367,12 @@ class Model(nn.Module):
         key = (B, N, str(dev))
         ws = self._ws.get(key)
         if ws is not None:
+            self._ws.move_to_end(key)
             return ws
+        while len(self._ws) >= self.max_cached_shapes:   # LRU: variable-length serving must not grow without bound
+            old_key, _ = self._ws.popitem(last=False)
+            for gk in [k for k in self._graphs if k[:2] == old_key[:2] and k[-1] == old_key[-1]]:
+                del self._graphs[gk]                      # graphs captured on the evicted workspace die with it
         D, G, inner = self.dim, self.wavenet_layers, self.inner
         Dp = _round_up(self.ff_inner, 128)
         bf, f32 = torch.bfloat16, torch.float32
@@ -355,7 +385,6 @@ class Model(nn.Module):
             "x_res": e(B, N, D, dt=f32),
             "qkv": e(B, N, 3 * inner), "attn_o": e(B, N, inner),
             "ff_g": e(B, N, Dp), "ff_c": e(B, N, Dp),
-            "out": e(B, N, D, dt=f32),
         }
         if self.condition_on_prompt:
             M = self.num_latents_m
@@ -423,7 +452,7 @@ class Model(nn.Module):
                                                                          dtype=torch.bfloat16))
         cond_proj = ops.gemm(c_bf, P["cond_w"], torch.empty(B, L, D, device=dev), n=D, epilogue=ops.EPI_F32,
                              bias=P["cond_b"])
-        return {"prompt_cond": prompt_cond, "tokens": tokens, "cond_proj": cond_proj, "length": length}
+        return Conditioning(prompt_cond=prompt_cond, tokens=tokens, cond_proj=cond_proj, length=length)
 
     def _run(self, name, fn, *args, **kwargs):
         """Call one kernel wrapper; when profiling is on, bracket it with CUDA events on the current stream."""
@@ -444,60 +473,80 @@ class Model(nn.Module):
         logits = self.forward(*args, cond_drop_prob=0., **kwargs)
         if cond_scale == 1.:
             return logits
-        logits = logits.clone()  # the output workspace is reused by the next call
         null_logits = self.forward(*args, cond_drop_prob=1., **kwargs)
-        return ops.cfg_combine(logits, null_logits, cond_scale, torch.empty_like(logits))
+        return ops.cfg_combine(logits, null_logits, cond_scale, logits)   # in place into the (fresh) first output
 
     @torch.no_grad()
-    def forward(self, x, times, prompt=None, prompt_mask=None, cond=None, cond_drop_prob=None,
-                _conditioning: Optional[dict] = None):
+    def forward(self, x, times, prompt=None, prompt_mask=None, cond=None, cond_drop_prob=None, *,
+                out: Optional[torch.Tensor] = None, _conditioning: Optional[dict] = None):
         """x (B, N, dim) fp32, times (B,) in [0, 1] -> (B, N, dim) fp32   (ns2.py:929-1000).
 
-        The returned tensor is a workspace owned by the model: it is overwritten by the next call with the
-        same (B, N).  Inference only (no autograd graph is recorded).
+        Returns a fresh tensor, like the reference; pass `out=` (contiguous fp32 (B, N, dim)) to have the prediction
+        written into a buffer the caller owns instead.  Inference only (no autograd graph is recorded).
 
         With `use_cuda_graphs` the whole step (every kernel launch below) is captured once per
-        (B, N, drop-prob, conditioning) and replayed; eligible when no RNG draw and no per-call host work is
+        (B, N, drop-prob, conditioning shapes) and replayed; eligible when no RNG draw and no per-call host work is
         involved, i.e. unconditional models or cached conditioning with cond_drop_prob in {0, 1}."""
+        if out is not None:
+            if not (out.is_cuda and out.dtype == torch.float32 and out.is_contiguous()
+                    and tuple(out.shape) == tuple(x.shape)):
+                raise ValueError("out must be a contiguous CUDA float32 tensor with x's shape")
         p_eff = self.cond_drop_prob if cond_drop_prob is None else cond_drop_prob
         if (self.use_cuda_graphs and self._prof is None and prompt_mask is None and x.is_cuda
+                and not torch.cuda.is_current_stream_capturing()
                 and (not self.condition_on_prompt or (_conditioning is not None and p_eff in (0, 0., 1, 1.)))):
-            return self._forward_graphed(x, times, p_eff, _conditioning)
-        return self._forward_impl(x, times, prompt, prompt_mask, cond, cond_drop_prob, _conditioning)
+            return self._forward_graphed(x, times, p_eff, _conditioning, out)
+        return self._forward_impl(x, times, prompt, prompt_mask, cond, cond_drop_prob, _conditioning, out)
 
-    def _forward_graphed(self, x, times, p_eff, conditioning):
+    def _forward_graphed(self, x, times, p_eff, conditioning, out):
         B, N, _ = x.shape
-        packed_before = self._packed
-        if self.packed() is not packed_before:
-            self._graphs.clear()  # parameters changed: captured graphs point at stale packed weights
-        key = (B, N, float(p_eff), id(conditioning), str(x.device))
+        self.packed()  # a parameter-version change invalidates the packed weights AND clears self._graphs
+        cond_sig = None
+        if conditioning is not None:
+            cond_sig = tuple(tuple(conditioning[k].shape) for k in ("prompt_cond", "tokens", "cond_proj"))
+        key = (B, N, float(p_eff), cond_sig, str(x.device))
         entry = self._graphs.get(key)
         if entry is None:
-            self.packed()
+            while len(self._graphs) >= 2 * self.max_cached_shapes:
+                self._graphs.popitem(last=False)
             xs = torch.empty(B, N, self.dim, device=x.device, dtype=torch.float32)
             ts = torch.empty(B, device=x.device, dtype=torch.float32)
+            static_out = torch.empty(B, N, self.dim, device=x.device, dtype=torch.float32)
+            static_cond = None
+            if conditioning is not None:   # static copies: the graph must not pin (or depend on) the caller's tensors
+                static_cond = Conditioning({k: (v.clone() if torch.is_tensor(v) else v) for k, v in conditioning.items()})
             xs.copy_(x)
             ts.copy_(times)
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):   # warm-up outside capture: workspaces, packing, lazy CUDA init
-                self._forward_impl(xs, ts, None, None, None, p_eff, conditioning)
+                self._forward_impl(xs, ts, None, None, None, p_eff, static_cond, static_out)
             torch.cuda.current_stream().wait_stream(side)
             graph = torch.cuda.CUDAGraph()
             # thread_local: other threads (e.g. the NCCL watchdog) may touch CUDA while this thread captures
             with torch.cuda.graph(graph, capture_error_mode="thread_local"):
-                out = self._forward_impl(xs, ts, None, None, None, p_eff, conditioning)
-            entry = (graph, xs, ts, out, conditioning)  # keeps the conditioning tensors alive
+                self._forward_impl(xs, ts, None, None, None, p_eff, static_cond, static_out)
+            entry = {"graph": graph, "xs": xs, "ts": ts, "out": static_out, "cond": static_cond,
+                     "cond_ref": weakref.ref(conditioning) if isinstance(conditioning, Conditioning) else None}
             self._graphs[key] = entry
-        graph, xs, ts, out, _ = entry
-        xs.copy_(x)
-        ts.copy_(times)
-        graph.replay()
+        else:
+            self._graphs.move_to_end(key)
+            if conditioning is not None and (entry["cond_ref"] is None or entry["cond_ref"]() is not conditioning):
+                for k, v in conditioning.items():    # a different (prompt, cond) of the same shapes: refresh the copies
+                    if torch.is_tensor(v):
+                        entry["cond"][k].copy_(v)
+                entry["cond_ref"] = weakref.ref(conditioning) if isinstance(conditioning, Conditioning) else None
+        entry["xs"].copy_(x)
+        entry["ts"].copy_(times)
+        entry["graph"].replay()
+        if out is None:
+            return entry["out"].clone()
+        out.copy_(entry["out"])
         return out
 
     @torch.no_grad()
     def _forward_impl(self, x, times, prompt=None, prompt_mask=None, cond=None, cond_drop_prob=None,
-                      _conditioning: Optional[dict] = None):
+                      _conditioning: Optional[dict] = None, out: Optional[torch.Tensor] = None):
         if prompt_mask is not None:
             raise NotImplementedError("prompt_mask is unsupported (the reference itself fails on it, SURVEY T9)")
         if not x.is_cuda:
@@ -517,27 +566,19 @@ class Model(nn.Module):
                       tc[1].weight.detach().float().contiguous(), tc[1].bias.detach().float().contiguous(),
                       t[:, :self.dim_time])
         c_tokens = None
-        x_add = None
+        cond_drop_mask = None
         if self.condition_on_prompt:
             if _conditioning is None:
                 assert _exists(prompt), "prompt is required when condition_on_prompt=True"
                 assert _exists(cond), "cond is required when condition_on_prompt=True"
                 _conditioning = self.precompute_conditioning(prompt, cond, N)
+            # two independent draws, in the reference's order (ns2.py:950, 980): kept in torch for RNG-stream parity
             drop_mask = _prob_mask_like((B,), cond_drop_prob, dev)
-            prompt_cond = torch.where(drop_mask[:, None], self.null_prompt_cond.detach().float(),
-                                      _conditioning["prompt_cond"])
-            t[:, self.dim_time:].copy_(prompt_cond)
-            c_tokens = torch.where(drop_mask[:, None, None], self.null_prompt_tokens.detach().float(),
-                                   _conditioning["tokens"])
             cond_drop_mask = _prob_mask_like((B,), cond_drop_prob, dev)
-            cproj = _conditioning["cond_proj"]  # (B, L, D) token-major
-            cproj = torch.where(cond_drop_mask[:, None, None], self.null_cond.detach().float().t()[None], cproj)
-            L = cproj.shape[1]
-            if L > N:
-                cproj = cproj[:, :N]
-            elif L < N:
-                cproj = torch.nn.functional.pad(cproj, (0, 0, 0, N - L))  # pad_or_curtail_to_length (ns2.py:70-77)
-            x_add = cproj.contiguous()
+            ops.select_rows(drop_mask, self.null_prompt_cond.detach().float().contiguous(),
+                            _conditioning["prompt_cond"], t[:, self.dim_time:])
+            c_tokens = ops.select_rows(drop_mask, self.null_prompt_tokens.detach().float().contiguous(),
+                                       _conditioning["tokens"], ws["c_bf"])
 
         # ---- all FiLM (gamma, beta) vectors in one GEMM ----
         self._run("cast", ops.cast_bf16, t, ws["t_bf"])
@@ -545,7 +586,12 @@ class Model(nn.Module):
                         bias=P["film_b"])[0]  # (B, rows)
 
         # ---- wavenet ----
-        x_bf = self._run("cast", ops.cast_bf16, x.float().contiguous(), ws["x_bf"], add=x_add)
+        if self.condition_on_prompt:
+            # x + pad_or_curtail(where(cond_drop_mask, null_cond, cond_proj)) -> bf16 in one pass (ns2.py:982-992)
+            x_bf = self._run("cast", ops.cond_inject, x.float().contiguous(), _conditioning["cond_proj"], ws["x_bf"],
+                             drop_mask=cond_drop_mask, null_cond=self.null_cond.detach().float().reshape(-1))
+        else:
+            x_bf = self._run("cast", ops.cast_bf16, x.float().contiguous(), ws["x_bf"])
         h = self._run("wn_init", ops.gemm, x_bf, P["wn_init_w"], ws["h"], n=D, epilogue=ops.EPI_BF16, bias=P["wn_init_b"],
                      segs=ops.conv3_segs(D))
         segs = ops.conv3_segs(D) + [(0, 3 * D, D, 0, 1)]
@@ -563,7 +609,6 @@ class Model(nn.Module):
 
         # ---- transformer ----
         if c_tokens is not None:
-            self._run("cast", ops.cast_bf16, c_tokens.contiguous(), ws["c_bf"])
             self._run("x_kv", ops.gemm, ws["c_bf"], P["x_kv_all"], ws["xkv"], n=self.depth * 2 * inner, epilogue=ops.EPI_BF16)
         qkv, ao = ws["qkv"], ws["attn_o"]
         Dp = ws["ff_g"].shape[-1]
@@ -592,4 +637,6 @@ class Model(nn.Module):
             self._run("ff_out", ops.gemm, ws["ff_c"], P[f"l{l}_ff_w2"], xr, n=D, epilogue=ops.EPI_F32, bias=P[f"l{l}_ff_b2"],
                      resid=xr)
         self._run("norm", ops.rmsnorm_film, xr, ws["h"], gamma=P["pred_gamma"])
-        return self._run("pred", ops.gemm, ws["h"], P["pred_w"], ws["out"], n=D, epilogue=ops.EPI_F32)
+        if out is None:
+            out = torch.empty(B, N, D, device=dev, dtype=torch.float32)   # fresh tensor, like the reference
+        return self._run("pred", ops.gemm, ws["h"], P["pred_w"], out, n=D, epilogue=ops.EPI_F32)

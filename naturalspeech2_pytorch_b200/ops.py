@@ -20,7 +20,12 @@ EPI_BF16, EPI_F32, EPI_GEGLU, EPI_WAVENET = NS2_EPI_BF16, NS2_EPI_F32, NS2_EPI_G
 Seg = Tuple[int, int, int, int, int]  # (a_col_off, b_col_off, k_len, shift_units, acc)
 
 
-def _stream() -> int:
+def _stream(t: Optional[torch.Tensor] = None) -> int:
+    """Raw handle of torch's current stream.  The library launches on the CURRENT device (tensor maps, kernel
+    attributes and the SM count are per device), so a tensor that lives elsewhere is rejected instead of being
+    launched on the wrong GPU — wrap the call in `torch.cuda.device(t.device)`."""
+    if t is not None and t.device.index != torch.cuda.current_device():
+        raise ValueError(f"tensor is on {t.device} but the current CUDA device is cuda:{torch.cuda.current_device()}")
     return torch.cuda.current_stream().cuda_stream
 
 
@@ -101,7 +106,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, n: int, epilogu
         args.film_batch_stride = film.stride(0)
     args.film = _ptr(film)
     args.film_group_stride = film_group_stride
-    check(lib.ns2_gemm(C.byref(args), _stream()), "ns2_gemm")
+    check(lib.ns2_gemm(C.byref(args), _stream(out)), "ns2_gemm")
     return out
 
 
@@ -116,7 +121,7 @@ def conv3_segs(k_len: int, tap_stride: Optional[int] = None, acc: int = 0, a_col
 # --------------------------------------------------------------------------------------------------
 # attention
 # --------------------------------------------------------------------------------------------------
-ATTN_AUTO, ATTN_ONE_TILE, ATTN_TWO_TILE, ATTN_TWO_TILE_POLY2, ATTN_TWO_TILE_POLY4 = 0, 1, 2, 3, 4
+ATTN_AUTO, ATTN_ONE_TILE, ATTN_TWO_TILE, ATTN_TWO_TILE_POLY2, ATTN_TWO_TILE_POLY4, ATTN_TWO_TILE_LOCKSTEP = 0, 1, 2, 3, 4, 5
 
 
 def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tensor, *, heads: int,
@@ -136,7 +141,7 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tens
     args.q_len, args.kv_len, args.dim_head = q.shape[1], k.shape[1], 64
     args.scale = float(scale if scale is not None else 64 ** -0.5)
     args.kernel = int(kernel)
-    check(lib.ns2_attn_fwd(C.byref(args), _stream()), "ns2_attn_fwd")
+    check(lib.ns2_attn_fwd(C.byref(args), _stream(out)), "ns2_attn_fwd")
     return out
 
 
@@ -159,7 +164,7 @@ def rmsnorm_film(x: torch.Tensor, out: torch.Tensor, *, gamma: Optional[torch.Te
         _req(film, torch.float32, "film")
         film_bs = film.stride(0)
     check(lib.ns2_rmsnorm_film(x.data_ptr(), D, B * N, D, N, _ptr(gamma), _ptr(film), film_bs,
-                               out.data_ptr(), D, _stream()), "ns2_rmsnorm_film")
+                               out.data_ptr(), D, _stream(out)), "ns2_rmsnorm_film")
     return out
 
 
@@ -226,6 +231,50 @@ def cast_bf16(x: torch.Tensor, out: torch.Tensor, add: Optional[torch.Tensor] = 
     return out
 
 
+def cond_inject(x: torch.Tensor, cproj: torch.Tensor, out: torch.Tensor, drop_mask: Optional[torch.Tensor] = None,
+                null_cond: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out (B, N, D) bf16 = x (B, N, D) f32 + [padded / curtailed, null-substituted] cproj (B, L, D) f32."""
+    lib = _lib.load()
+    _req(x, torch.float32, "x")
+    _req(cproj, torch.float32, "cproj")
+    _req(out, torch.bfloat16, "out")
+    B, N, D = x.shape
+    if not (x.is_contiguous() and cproj.is_contiguous() and out.is_contiguous()) or cproj.shape[0] != B \
+            or cproj.shape[2] != D or out.shape != x.shape:
+        raise ValueError("cond_inject: x/out (B, N, D) and cproj (B, L, D) must be contiguous and consistent")
+    if drop_mask is not None:
+        if drop_mask.dtype != torch.bool or drop_mask.numel() != B or not drop_mask.is_cuda:
+            raise ValueError("drop_mask must be a CUDA bool tensor of B elements")
+        _req(null_cond, torch.float32, "null_cond")
+        if null_cond.numel() != D or not null_cond.is_contiguous():
+            raise ValueError("null_cond must be a contiguous (D,) float tensor")
+    check(lib.ns2_cond_inject(x.data_ptr(), cproj.data_ptr(), _ptr(drop_mask), _ptr(null_cond), B, N, cproj.shape[1], D,
+                              out.data_ptr(), _stream(out)), "ns2_cond_inject")
+    return out
+
+
+def select_rows(drop_mask: torch.Tensor, null_row: torch.Tensor, src: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+    """out[b] = null_row if drop_mask[b] else src[b]; src/out are (B, ...) with contiguous trailing dims; out may be a
+    column slice of a wider f32 matrix (row stride > row length) or a bf16 tensor."""
+    lib = _lib.load()
+    _req(null_row, torch.float32, "null_row")
+    _req(src, torch.float32, "src")
+    B = src.shape[0]
+    row_len = src.numel() // B
+    if drop_mask.dtype != torch.bool or drop_mask.numel() != B or not drop_mask.is_cuda:
+        raise ValueError("drop_mask must be a CUDA bool tensor of B elements")
+    if null_row.numel() != row_len or not null_row.is_contiguous() or not src.is_contiguous():
+        raise ValueError("null_row must hold one row; src must be contiguous")
+    if out.dtype not in (torch.float32, torch.bfloat16) or out.shape[0] != B or out.numel() != B * row_len:
+        raise ValueError("out must be (B, ...) f32/bf16 with src's row length")
+    if out.dim() > 2 and not out.is_contiguous():
+        raise ValueError("multi-dimensional out must be contiguous")
+    check(lib.ns2_select_rows(drop_mask.data_ptr(), null_row.data_ptr(), src.data_ptr(), row_len, B, row_len,
+                              out.data_ptr(), out.stride(0), int(out.dtype == torch.bfloat16), _stream(out)),
+          "ns2_select_rows")
+    return out
+
+
 def mean_rows(x: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
     lib = _lib.load()
     _req(x, torch.float32, "x")
@@ -267,14 +316,21 @@ def q_sample(x0, noise, alpha, sigma, x_t, target=None, objective: str = "v"):
     return x_t, target
 
 
-def mse_rows(pred, target, out, scratch=None):
+def mse_rows(pred, target, out, scratch=None, mean_out=None):
+    """out[b] = mean((pred[b] - target[b])^2); `mean_out` (0-d / 1-element f32) additionally receives out.mean()."""
     lib = _lib.load()
     B = pred.shape[0]
     per = pred.numel() // B
+    for name, t in (("pred", pred), ("target", target), ("out", out)):
+        _req(t, torch.float32, name)
+    if not (pred.is_contiguous() and target.is_contiguous()):
+        raise ValueError("pred and target must be contiguous")
     if scratch is None:
         scratch = torch.empty(B * NS2_MSE_SCRATCH_PER_SAMPLE, device=pred.device, dtype=torch.float32)
+    if mean_out is not None:
+        _req(mean_out, torch.float32, "mean_out")
     check(lib.ns2_mse_rows(pred.data_ptr(), target.data_ptr(), B, per, scratch.data_ptr(),
-                           out.data_ptr(), _stream()), "ns2_mse_rows")
+                           out.data_ptr(), _ptr(mean_out), _stream()), "ns2_mse_rows")
     return out
 
 
@@ -288,6 +344,18 @@ def ddim_step(x, v, alpha, sigma, alpha_next, sigma_next, objective: str = "v"):
                             _stream()),
           "ns2_ddim_step")
     return x
+
+
+def x_start_from_pred(x, pred, alpha, sigma, out, objective: str = "v"):
+    """x_start implied by the model output under the chosen parameterisation (ns2.py:1673-1680)."""
+    lib = _lib.load()
+    B = x.shape[0]
+    per = x.numel() // B
+    for name, t in (("x", x), ("pred", pred), ("alpha", alpha), ("sigma", sigma), ("out", out)):
+        _req(t, torch.float32, name)
+    check(lib.ns2_x_start(x.data_ptr(), pred.data_ptr(), alpha.data_ptr(), sigma.data_ptr(), B, per, out.data_ptr(),
+                          OBJECTIVES[objective], _stream(out)), "ns2_x_start")
+    return out
 
 
 def cfg_combine(cond, null, scale, out):
@@ -326,8 +394,11 @@ def rvq_encode(frames: torch.Tensor, codebooks: torch.Tensor, prepared, codes: O
     F = fr.shape[0]
     if codes is None:
         codes = torch.empty((F, Q), device=fr.device, dtype=torch.int64)
+    if stats is not None and not (stats.is_cuda and stats.dtype == torch.int64 and stats.is_contiguous()
+                                  and stats.numel() >= _lib.NS2_RVQ_STATS_LEN):
+        raise ValueError(f"stats must be a contiguous CUDA int64 tensor with >= {_lib.NS2_RVQ_STATS_LEN} elements")
     check(lib.ns2_rvq_encode(fr.data_ptr(), F, D, cb.data_ptr(), cb16.data_ptr(), cn2.data_ptr(),
-                             meta.data_ptr(), Q, K, codes.data_ptr(), _ptr(stats), _stream()),
+                             meta.data_ptr(), Q, K, codes.data_ptr(), _ptr(stats), _stream(codes)),
           "ns2_rvq_encode")
     return codes
 
@@ -343,3 +414,22 @@ def rvq_decode(codes: torch.Tensor, codebooks: torch.Tensor, out: Optional[torch
     check(lib.ns2_rvq_decode(cd.data_ptr(), F, Q, K, D, cb.data_ptr(), out.data_ptr(), _stream()),
           "ns2_rvq_decode")
     return out
+
+
+def rvq_ce(frames: torch.Tensor, codebooks: torch.Tensor, cn2: torch.Tensor, own_codes: torch.Tensor,
+           target_codes: torch.Tensor) -> torch.Tensor:
+    """Cross-entropy head of the residual VQ (`codec.rq`): frames (F, 128) f32, codes (F, Q) int64 -> 0-d loss."""
+    lib = _lib.load()
+    _req(frames, torch.float32, "frames")
+    cb = codebooks.contiguous()
+    Q, K, D = cb.shape
+    fr = frames.contiguous()
+    F = fr.shape[0]
+    for name, t in (("own_codes", own_codes), ("target_codes", target_codes)):
+        if not (t.is_cuda and t.dtype == torch.int64 and t.is_contiguous() and tuple(t.shape) == (F, Q)):
+            raise ValueError(f"{name} must be a contiguous CUDA int64 tensor of shape (F, Q)")
+    scratch = torch.empty(F * Q, device=fr.device, dtype=torch.float32)
+    loss = torch.empty((), device=fr.device, dtype=torch.float32)
+    check(lib.ns2_rvq_ce(fr.data_ptr(), F, D, cb.data_ptr(), cn2.data_ptr(), Q, K, own_codes.data_ptr(),
+                         target_codes.data_ptr(), scratch.data_ptr(), loss.data_ptr(), _stream(fr)), "ns2_rvq_ce")
+    return loss

@@ -84,3 +84,40 @@ def test_conditional_requires_conditioning():
     assert torch.isfinite(loss)
     out = ns.sample(length=160, prompt_enc=prompt, cond=cond, cond_scale=1.5)
     assert out.shape == (2, 160, 128) and torch.isfinite(out).all()
+
+
+def test_sampler_graph_matches_eager_loop():
+    """The captured sampling step (forward(s) + guidance + DDIM update in one CUDA graph, schedule tables) gives the
+    same latents as the eager per-step loop, for unconditional and guided conditional sampling."""
+    from naturalspeech2_pytorch_b200 import NaturalSpeech2
+    for name, kw in (("uncond_small", {}), ("cond_small", dict(cond_scale=2.0))):
+        z, kwargs, seed = load_model_golden(name)
+        model = build_model(kwargs, seed, device="cuda")
+        extra = {}
+        if kwargs.get("condition_on_prompt"):
+            extra = dict(prompt_enc=torch.from_numpy(z["in_prompt"]).cuda(), cond=torch.from_numpy(z["in_cond"]).cuda())
+        noise = torch.randn(2, 160, 128, generator=torch.Generator().manual_seed(5))
+        outs = []
+        for graphs in (False, True):
+            ns = NaturalSpeech2(model, target_sample_hz=24000, timesteps=3, cuda_graphs=graphs)
+            outs.append(ns.sample(length=160, batch_size=2, noise=noise, **extra, **kw))
+        assert torch.equal(outs[0], outs[1]), name
+        # a second call with other noise reuses the captured graph
+        ns.sample(length=160, batch_size=2, **extra, **kw)
+        assert len(ns._sampler_graphs) == 1
+
+
+def test_loss_with_rvq_cross_entropy_term():
+    """rvq_cross_entropy_loss_weight != 0 adds weight * codec.rq(x_start, codes)[1] (ns2.py:1670-1684)."""
+    from naturalspeech2_pytorch_b200 import EncodecRVQ, NaturalSpeech2
+    _, kwargs, seed = load_model_golden("uncond_small")
+    model = build_model(kwargs, seed, device="cuda")
+    codec = EncodecRVQ(torch.randn(4, 256, 128, generator=torch.Generator().manual_seed(1))).cuda()
+    g = torch.Generator().manual_seed(2)
+    latents = torch.randn(2, 160, 128, generator=g).cuda()
+    codes, _ = codec.quantize(latents)
+    times, noise = torch.rand(2, generator=g), torch.randn(2, 160, 128, generator=g)
+    base = NaturalSpeech2(model, codec, timesteps=4)(latents, codes=codes, times=times, noise=noise)
+    with_ce = NaturalSpeech2(model, codec, timesteps=4, rvq_cross_entropy_loss_weight=0.5)(
+        latents, codes=codes, times=times, noise=noise)
+    assert torch.isfinite(with_ce) and float(with_ce) > float(base)

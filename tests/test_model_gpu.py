@@ -161,3 +161,60 @@ def test_large_batch_is_chunked_in_the_small_layers():
     full = model(x, t).clone()
     part = torch.cat([model(x[:48], t[:48]).clone(), model(x[48:], t[48:]).clone()])
     assert torch.equal(full, part)
+
+
+def test_outputs_are_fresh_tensors_and_out_argument():
+    """Reference semantics: every forward returns its own tensor (two predictions can be held at once); `out=` writes
+    into a caller-owned buffer; both also under CUDA-graph replay."""
+    _, kwargs, seed = load_model_golden("uncond_small")
+    model = build_model(kwargs, seed, device="cuda")
+    x1, x2 = torch.randn(2, 128, 128, device="cuda"), torch.randn(2, 128, 128, device="cuda")
+    t = torch.rand(2, device="cuda")
+    for graphs in (False, True):
+        model.use_cuda_graphs = graphs
+        a = model(x1, t)
+        a_copy = a.clone()
+        b = model(x2, t)
+        assert a.data_ptr() != b.data_ptr() and torch.equal(a, a_copy) and not torch.equal(a, b)
+        buf = torch.empty_like(x1)
+        c = model(x1, t, out=buf)
+        assert c.data_ptr() == buf.data_ptr() and torch.equal(c, a)
+
+
+def test_data_updates_need_invalidate_packed():
+    """`.data` updates (EMA-style lerp_) do not bump the version counter: `invalidate_packed()` makes them visible,
+    also to captured graphs."""
+    _, kwargs, seed = load_model_golden("uncond_small")
+    m1 = build_model(kwargs, seed, device="cuda")
+    m2 = build_model(kwargs, seed + 1, device="cuda")
+    x, t = torch.randn(1, 128, 128, device="cuda"), torch.rand(1, device="cuda")
+    m1.use_cuda_graphs = True
+    before = m1(x, t)
+    with torch.no_grad():
+        for p, q in zip(m1.parameters(), m2.parameters()):
+            p.data.copy_(q.data)
+    m1.invalidate_packed()
+    after = m1(x, t)
+    assert torch.equal(after, m2(x, t)) and not torch.equal(after, before)
+
+
+def test_partial_condition_dropout_matches_composition():
+    """0 < cond_drop_prob < 1: the two Bernoulli masks are drawn in the reference's order (ns2.py:950, 980); the
+    output equals, sample by sample, the fully-conditioned or fully-null forward selected by those masks."""
+    z, kwargs, seed = load_model_golden("cond_small")
+    model = build_model(kwargs, seed, device="cuda")
+    inp = golden_inputs(z, kwargs)
+    x, times = inp["x"].cuda().repeat(4, 1, 1), inp["times"].cuda().repeat(4)
+    prompt, cond = inp["prompt"].cuda().repeat(4, 1, 1), inp["cond"].cuda().repeat(4, 1, 1)
+    B = x.shape[0]
+    torch.manual_seed(123)
+    out = model(x, times, prompt=prompt, cond=cond, cond_drop_prob=0.5)
+    torch.manual_seed(123)
+    m_prompt = torch.zeros((B,), device="cuda").float().uniform_(0, 1) < 0.5
+    m_cond = torch.zeros((B,), device="cuda").float().uniform_(0, 1) < 0.5
+    keep = model(x, times, prompt=prompt, cond=cond, cond_drop_prob=0.)
+    null = model(x, times, prompt=prompt, cond=cond, cond_drop_prob=1.)
+    both = m_prompt == m_cond          # samples where both masks agree can be compared with the pure forwards
+    assert bool(both.any()) and bool((~m_prompt & both).any()) and bool((m_prompt & both).any())
+    ref = torch.where(m_prompt[:, None, None], null, keep)
+    assert torch.equal(out[both], ref[both])

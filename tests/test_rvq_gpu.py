@@ -88,3 +88,29 @@ def test_rvq_full_size_properties():
     idx = torch.randperm(F, generator=torch.Generator().manual_seed(0))[:65536]
     ref = rvq_oracle.encode(x[idx.cuda()].cpu().numpy(), cb.numpy())
     np.testing.assert_array_equal(codes[idx.cuda()].cpu().numpy(), ref)
+
+
+def test_rq_cross_entropy_head_matches_torch():
+    """`codec.rq(x, codes)` (ns2.py:1682; vector-quantize-pytorch ResidualVQ with indices): per stage logits =
+    -cdist(residual, codebook), cross-entropy against the given codes (ignore_index -1), summed over stages, residual
+    chain through the codec's own nearest codewords.  Checked against that formula written with torch ops in fp64."""
+    from naturalspeech2_pytorch_b200 import EncodecRVQ
+    g = torch.Generator().manual_seed(21)
+    Q, K = 4, 256
+    cb = torch.randn(Q, K, 128, generator=g)
+    x = torch.randn(3, 50, 128, generator=g)
+    codes = torch.randint(0, K, (3, 50, Q), generator=g)
+    codes[0, :5, 1] = -1                                   # ignored targets
+    codec = EncodecRVQ(cb).cuda()
+    quantized, loss = codec.rq(x.cuda(), codes.cuda())
+    own, emb = codec.quantize(x.cuda())
+    assert torch.equal(quantized, emb)
+    r = x.reshape(-1, 128).double()
+    cbd = cb.double()
+    own_c = own.reshape(-1, Q).cpu()
+    total = 0.0
+    for q in range(Q):
+        logits = -torch.cdist(r, cbd[q])
+        total = total + torch.nn.functional.cross_entropy(logits, codes.reshape(-1, Q)[:, q], ignore_index=-1)
+        r = r - cbd[q][own_c[:, q]]
+    assert abs(float(loss) - float(total)) < 1e-4 * max(1.0, abs(float(total))), (float(loss), float(total))

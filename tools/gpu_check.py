@@ -261,7 +261,8 @@ def run_attn():
     dev = "cuda"
     ok = True
     names = {ops.ATTN_AUTO: "auto", ops.ATTN_ONE_TILE: "one-tile", ops.ATTN_TWO_TILE: "two-tile",
-             ops.ATTN_TWO_TILE_POLY2: "two-tile/poly2", ops.ATTN_TWO_TILE_POLY4: "two-tile/poly4"}
+             ops.ATTN_TWO_TILE_POLY2: "two-tile/poly2", ops.ATTN_TWO_TILE_POLY4: "two-tile/poly4",
+             ops.ATTN_TWO_TILE_LOCKSTEP: "two-tile/lockstep"}
     shapes = [(1, 1, 128, 128), (2, 8, 1024, 1024), (2, 8, 256, 32), (2, 8, 32, 135), (1, 2, 200, 300),
               (3, 4, 513, 700), (40, 8, 1024, 1024)]
     for kern in names:
@@ -294,7 +295,8 @@ def run_attn():
     qkv = torch.randn(B, N, 3 * inner, device=dev).bfloat16()
     out = torch.empty(B, N, inner, device=dev, dtype=torch.bfloat16)
     flops = 4.0 * B * H * N * N * 64
-    for kern in (ops.ATTN_ONE_TILE, ops.ATTN_TWO_TILE, ops.ATTN_TWO_TILE_POLY2, ops.ATTN_TWO_TILE_POLY4):
+    for kern in (ops.ATTN_ONE_TILE, ops.ATTN_TWO_TILE_LOCKSTEP, ops.ATTN_TWO_TILE, ops.ATTN_TWO_TILE_POLY2,
+                 ops.ATTN_TWO_TILE_POLY4):
         args = (qkv[:, :, :inner], qkv[:, :, inner:2 * inner], qkv[:, :, 2 * inner:], out)
         for _ in range(3):
             ops.attention(*args, heads=H, kernel=kern)
