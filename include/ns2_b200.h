@@ -91,7 +91,10 @@ typedef struct ns2_gemm_args {
   const float* film;       /* WAVENET: FiLM table */
   int64_t film_batch_stride;
   int32_t film_group_stride;
+  int32_t flags;           /* 0, or NS2_GEMM_FLAG_* */
 } ns2_gemm_args;
+
+#define NS2_GEMM_FLAG_SKIP_EPILOGUE 1  /* measurement aid: run the TMA/MMA mainloop only, write nothing (CTA-pair kernel) */
 
 int ns2_gemm(const ns2_gemm_args* args, ns2_stream_t stream);
 
@@ -109,6 +112,8 @@ typedef struct ns2_attn_args {
   int32_t batches, heads, q_len, kv_len, dim_head;
   float scale;
   int32_t kernel;   /* NS2_ATTN_AUTO, or force one implementation (tests / tuning) */
+  void* debug_timeline; /* bring-up aid, normally NULL: device buffer of 64*16 int64 receiving clock64 stamps of CTA 0
+                           of the two-tile kernel (tools/attn_timeline.py) */
 } ns2_attn_args;
 
 #define NS2_ATTN_AUTO 0            /* two-tile kernel when q_len > 128 and kv_len > 64, else one-tile */

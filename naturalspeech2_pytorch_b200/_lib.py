@@ -37,6 +37,7 @@ class GemmArgs(C.Structure):
         ("out", C.c_void_p), ("out_row_stride", C.c_int64),
         ("resid", C.c_void_p), ("resid_row_stride", C.c_int64),
         ("film", C.c_void_p), ("film_batch_stride", C.c_int64), ("film_group_stride", C.c_int32),
+        ("flags", C.c_int32),
     ]
 
 
@@ -48,6 +49,7 @@ class AttnArgs(C.Structure):
         ("out", C.c_void_p), ("o_row_stride", C.c_int64), ("o_batch_stride", C.c_int64),
         ("batches", C.c_int32), ("heads", C.c_int32), ("q_len", C.c_int32), ("kv_len", C.c_int32),
         ("dim_head", C.c_int32), ("scale", C.c_float), ("kernel", C.c_int32),
+        ("debug_timeline", C.c_void_p),
     ]
 
 

@@ -344,7 +344,14 @@ struct Attn2Dev {
   int q_len, kv_len, heads;
   int q_pairs, num_items;
   float scale_log2e;
+  long long* timeline;   // bring-up aid (ns2_attn_args.debug_timeline): clock64 stamps of CTA 0, else NULL
 };
+
+// timeline layout: [tile g < 64][16 slots]; softmax warp 0 / warp 4 lane 0 and the MMA thread of CTA 0 write
+#define NS2_ATT_STAMP(slot)                                                                          \
+  do {                                                                                               \
+    if (p.timeline != nullptr && blockIdx.x == 0 && g < 64) p.timeline[g * 16 + (slot)] = clock64(); \
+  } while (0)
 
 __device__ __forceinline__ float fmax3(float a, float b, float c) {
   float r;
@@ -465,42 +472,48 @@ __global__ void __launch_bounds__(attn2::THREADS, 1) attn2_fwd_kernel(const __gr
   // registers; the auxiliary warpgroup gives its share up
   if (warp >= 8) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    // Both service warps run their loops CONVERGED (all 32 lanes, warp-uniform operands) and elect one lane per
+    // asynchronous instruction: tcgen05.mma / TMA take their operands from uniform registers, and when they are issued
+    // from a single-lane divergent region the compiler wraps each one in an ELECT / R2UR / BRA.U.ANY loop that costs
+    // ~117 cycles per instruction (profiles/r02_ubench_mma.txt) — more than the MMA itself.
     if (warp == 8) {
-    // ================================ TMA producer ================================
-    if (lane == 0) {
+      // ================================ TMA producer ================================
       uint32_t g = 0;  // global key-tile counter of this CTA
       for (int it = 0; it < my_items; ++it) {
         int b, head, q0;
         decode(it, b, head, q0);
         const int qs = it & 1;
         mbar_wait(smem_u32(&q_empty[qs]), ((it >> 1) & 1) ^ 1);
-        const uint32_t qb = smem_u32(&q_full[qs]);
-        mbar_arrive_expect_tx(qb, 2 * Q_BYTES);
-        tma_load_3d(smem_u32(smem + OFF_Q + (qs * 2 + 0) * Q_BYTES), &p.tmQ, qb, head * DH, q0, b);
-        tma_load_3d(smem_u32(smem + OFF_Q + (qs * 2 + 1) * Q_BYTES), &p.tmQ, qb, head * DH, q0 + BQ, b);
+        if (elect_one()) {
+          const uint32_t qb = smem_u32(&q_full[qs]);
+          mbar_arrive_expect_tx(qb, 2 * Q_BYTES);
+          tma_load_3d(smem_u32(smem + OFF_Q + (qs * 2 + 0) * Q_BYTES), &p.tmQ, qb, head * DH, q0, b);
+          tma_load_3d(smem_u32(smem + OFF_Q + (qs * 2 + 1) * Q_BYTES), &p.tmQ, qb, head * DH, q0 + BQ, b);
+        }
+        __syncwarp();
         for (int j = 0; j < T; ++j, ++g) {
           const int st = g % KVS;
           mbar_wait(smem_u32(&kv_empty[st]), ((g / KVS) & 1) ^ 1);
-          const uint32_t fb = smem_u32(&kv_full[st]);
-          mbar_arrive_expect_tx(fb, 2 * KV_BYTES);
-          tma_load_3d(smem_u32(smem + OFF_K + st * KV_BYTES), &p.tmK, fb, head * DH, j * BKV, b);
-          tma_load_3d(smem_u32(smem + OFF_V + st * KV_BYTES), &p.tmV, fb, head * DH, j * BKV, b);
+          if (elect_one()) {
+            const uint32_t fb = smem_u32(&kv_full[st]);
+            mbar_arrive_expect_tx(fb, 2 * KV_BYTES);
+            tma_load_3d(smem_u32(smem + OFF_K + st * KV_BYTES), &p.tmK, fb, head * DH, j * BKV, b);
+            tma_load_3d(smem_u32(smem + OFF_V + st * KV_BYTES), &p.tmV, fb, head * DH, j * BKV, b);
+          }
+          __syncwarp();
         }
       }
-    }
     } else if (warp == 9) {
-    // ================================ MMA issuer ==================================
-    if (lane == 0) {
+      // ================================ MMA issuer ==================================
       constexpr uint32_t idesc_s = umma_idesc_f16(BQ, BKV, 1, 0, 0);
       constexpr uint32_t idesc_o = umma_idesc_f16(BQ, DH, 1, 0, /*V is MN-major*/ 1);
       const int total = my_items * T;
       // S for global tile gs (item gs / T, key tile gs % T), both warpgroups
       auto issue_s = [&](int gs) {
+        const int g = gs;   // for NS2_ATT_STAMP
         const int it = gs / T, j = gs - it * T;
         const int qs = it & 1;
-        if (j == 0) {
-          mbar_wait(smem_u32(&q_full[qs]), (it >> 1) & 1);
-        }
+        if (j == 0) mbar_wait(smem_u32(&q_full[qs]), (it >> 1) & 1);
         const int st = gs % KVS;
         mbar_wait(smem_u32(&kv_full[st]), (gs / KVS) & 1);
         tc_fence_after();
@@ -512,12 +525,19 @@ __global__ void __launch_bounds__(attn2::THREADS, 1) attn2_fwd_kernel(const __gr
             tc_fence_after();
           }
           const uint64_t dq = umma_desc_sw128(smem_u32(smem + OFF_Q + (qs * 2 + w) * Q_BYTES), 16, 1024);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < DH / 16; ++k)
-            tc_mma_f16(tmem_base + TM_S + w * BKV, dq + 2 * k, dk + 2 * k, idesc_s, k > 0);
-          tc_commit(smem_u32(&s_full[w]));
+            for (int k = 0; k < DH / 16; ++k)
+              tc_mma_f16(tmem_base + TM_S + w * BKV, dq + 2 * k, dk + 2 * k, idesc_s, k > 0);
+            tc_commit(smem_u32(&s_full[w]));
+            NS2_ATT_STAMP(12 + w);
+          }
+          __syncwarp();
         }
-        if (j == T - 1) tc_commit(smem_u32(&q_empty[qs]));  // every S of this item has been issued
+        if (j == T - 1) {
+          if (elect_one()) tc_commit(smem_u32(&q_empty[qs]));  // every S of this item has been issued
+          __syncwarp();
+        }
       };
       if (total > 0) issue_s(0);
       for (int g = 0; g < total; ++g) {
@@ -529,18 +549,22 @@ __global__ void __launch_bounds__(attn2::THREADS, 1) attn2_fwd_kernel(const __gr
         for (int w = 0; w < 2; ++w) {
           mbar_wait(smem_u32(&p_full[w]), g & 1);
           tc_fence_after();
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < BKV / 16; ++k) {
-            // A = P^w from TMEM: 16 keys = 8 packed columns per step; B = V: 16 keys = 2048 bytes per step
-            const uint64_t dv = umma_desc_sw128(vbase + k * 2048, 1024, 1024);
-            tc_mma_f16_ts(tmem_base + TM_O + w * DH, tmem_base + TM_P + w * (BKV / 2) + k * 8, dv, idesc_o,
-                          (j > 0) | (k > 0));
+            for (int k = 0; k < BKV / 16; ++k) {
+              // A = P^w from TMEM: 16 keys = 8 packed columns per step; B = V: 16 keys = 2048 bytes per step
+              const uint64_t dv = umma_desc_sw128(vbase + k * 2048, 1024, 1024);
+              tc_mma_f16_ts(tmem_base + TM_O + w * DH, tmem_base + TM_P + w * (BKV / 2) + k * 8, dv, idesc_o,
+                            (j > 0) | (k > 0));
+            }
+            tc_commit(smem_u32(&o_full[w]));
+            NS2_ATT_STAMP(14 + w);
           }
-          tc_commit(smem_u32(&o_full[w]));
+          __syncwarp();
         }
-        tc_commit(smem_u32(&kv_empty[st]));
+        if (elect_one()) tc_commit(smem_u32(&kv_empty[st]));
+        __syncwarp();
       }
-    }
     }
   } else {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
@@ -560,8 +584,11 @@ __global__ void __launch_bounds__(attn2::THREADS, 1) attn2_fwd_kernel(const __gr
       decode(it, b, head, q0);
       float m_run = -INFINITY, l_run = 0.f;
       for (int j = 0; j < T; ++j, ++g) {
+        const bool stamp = (qw == 0 && lane == 0);
+        if (stamp) NS2_ATT_STAMP(w * 6 + 0);
         mbar_wait(smem_u32(&s_full[w]), g & 1);
         tc_fence_after();
+        if (stamp) NS2_ATT_STAMP(w * 6 + 1);
         float s[BKV];
         {
           uint32_t r0[32], r1[32], r2[32], r3[32];
@@ -581,6 +608,7 @@ __global__ void __launch_bounds__(attn2::THREADS, 1) attn2_fwd_kernel(const __gr
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&s_free[w]));   // S^w may be overwritten by the next tile's MMA
+        if (stamp) NS2_ATT_STAMP(w * 6 + 2);
         const int valid = p.kv_len - j * BKV;
         if (valid < BKV) {  // padding keys of the last tile (TMA zero-filled): exclude them
 #pragma unroll
@@ -631,11 +659,13 @@ __global__ void __launch_bounds__(attn2::THREADS, 1) attn2_fwd_kernel(const __gr
             mbar_wait(smem_u32(&turn[qw]), g & 1);
           }
         }
+        if (stamp) NS2_ATT_STAMP(w * 6 + 3);
         // the P buffer is read by the previous tile's P.V until o_full flips (long done by now)
         if (j > 0) {
           mbar_wait(smem_u32(&o_full[w]), (g - 1) & 1);
           tc_fence_after();
         }
+        if (stamp) NS2_ATT_STAMP(w * 6 + 4);
         // P = exp2(s*c - m) -> bf16 pairs; row sum in fp32
         const unsigned long long nm2 = pack_f32x2(-m_run, -m_run);
         unsigned long long lsum0 = 0ull, lsum1 = 0ull;  // two packed (0.f, 0.f) accumulators
@@ -685,6 +715,7 @@ __global__ void __launch_bounds__(attn2::THREADS, 1) attn2_fwd_kernel(const __gr
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&p_full[w]));
+        if (stamp) NS2_ATT_STAMP(w * 6 + 5);
       }
       // ---- epilogue of the work item: O / l -> bf16 -> global ----
       mbar_wait(smem_u32(&o_full[w]), (g - 1) & 1);
@@ -806,6 +837,7 @@ extern "C" int ns2_attn_fwd(const ns2_attn_args* a, ns2_stream_t stream_) {
   d2.q_pairs = (a->q_len + 2 * attn2::BQ - 1) / (2 * attn2::BQ);
   d2.num_items = d2.q_pairs * a->heads * a->batches;
   d2.scale_log2e = a->scale * 1.4426950408889634f;
+  d2.timeline = reinterpret_cast<long long*>(a->debug_timeline);
   const int grid2 = d2.num_items < num_sms() ? d2.num_items : num_sms();
   auto launch2 = [&](auto kern) -> int {
     NS2_CUDA_CHECK(set_max_smem_once(kern, attn2::SMEM_BYTES));

@@ -23,7 +23,6 @@
 #include "../../include/ns2_b200.h"
 
 #include <atomic>
-#include <stdlib.h>
 
 namespace ns2 {
 
@@ -52,14 +51,8 @@ struct GemmDev {
   const float* film;
   long long film_bs;
   int film_gs;
-  int debug;  // NS2_GEMM_DEBUG bits (bring-up only): 1 = skip global stores, 2 = skip TMEM loads, 4 = skip epilogue
+  int skip_epilogue;  // measurement aid (ns2_gemm_args.flags & NS2_GEMM_FLAG_SKIP_EPILOGUE): mainloop-only timing
 };
-
-__device__ long long g_gemm_dbg[16 * 64];  // bring-up timeline: [tile][slot] clock64 stamps of pair 0 (NS2_GEMM_DEBUG & 8)
-#define NS2_DBG_STAMP(slot)                                                             \
-  do {                                                                                \
-    if ((p.debug & 8) && pair == 0 && leader && ti < 64) g_gemm_dbg[ti * 16 + (slot)] = clock64(); \
-  } while (0)
 
 struct TileCoord {
   int g, b, n0, n_tile;
@@ -141,13 +134,7 @@ __device__ __forceinline__ void epi_plain_chunk(const GemmDev& p, const TileCoor
                                                 uint32_t taddr, bool row_ok, long long grow) {
   const int col0 = tile_col0 + tc;
   float v[W];
-  if (p.debug & 2) {
-#pragma unroll
-    for (int i = 0; i < W; ++i) v[i] = 1.0f;
-  } else {
-    tmem_load_f32<W>(taddr + tc, v);
-  }
-  if (p.debug & 1) row_ok = row_ok && (v[0] == 123456.0f);
+  tmem_load_f32<W>(taddr + tc, v);
   if (p.bias != nullptr) add_vec<W>(v, p.bias + t.g * p.b_grs + col0);
   if (!row_ok) return;
   if constexpr (EPI == NS2_EPI_BF16) {
@@ -253,8 +240,8 @@ struct Stager {
   uint32_t count;     // boxes issued so far
   int lane;
   __device__ __forceinline__ uint32_t acquire() {
-    // the box used two stores ago must have been read out by the TMA engine
-    if (lane == 0) tma_store_wait_read<1>();
+    // the box used two stores ago must have been read out by the TMA engine (bulk groups belong to the elected lane)
+    if (elect_one()) tma_store_wait_read<1>();
     __syncwarp();
     return base + (count & 1) * STG_BYTES;
   }
@@ -267,11 +254,12 @@ struct Stager {
   __device__ __forceinline__ void submit(const CUtensorMap* m, uint32_t box, int c0, int c1, int c2, bool reduce) {
     fence_proxy_async_smem();
     __syncwarp();
-    if (lane == 0) {
+    if (elect_one()) {   // converged warp + elected lane: no per-instruction uniformisation loop (see gemm_kernel)
       if (reduce) tma_reduce_add_3d(m, box, c0, c1, c2);
       else tma_store_3d(m, box, c0, c1, c2);
       tma_store_commit();
     }
+    __syncwarp();
     ++count;
   }
 };
@@ -445,67 +433,74 @@ __global__ void __launch_bounds__(256, 1) gemm_kernel(const __grid_constant__ Ge
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
 
+  // The two service warps run CONVERGED (all 32 lanes execute the loops on warp-uniform values) and elect one lane per
+  // TMA / tcgen05 instruction.  Issued from a single-lane divergent region, every UTMALDG / UTCHMMA is wrapped by the
+  // compiler in an ELECT / R2UR / BRA.U.ANY loop costing ~117 cycles (profiles/r02_ubench_mma.txt): 4 MMAs per k-block
+  // then take 468 cycles to ISSUE against 512 cycles of tensor work, which is what capped round 1's mainloop.
   if (warp == 0) {
     // =============================== TMA producer ===============================
-    if (lane == 0) {
-      uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        const TileCoord t = decode_tile<BM>(p, tile);
-        const int dil = p.dil[t.g];
-        for (int s = 0; s < p.num_segs; ++s) {
-          const ns2_gemm_seg sg = p.segs[s];
-          const int row0 = t.n0 - sg.shift_units * dil;
-          const int a_c0 = t.g * p.a_gcs + sg.a_col_off;
-          const int b_r0 = t.g * p.b_grs + t.n_tile * BN;
-          const int kblocks = (sg.k_len + BK - 1) / BK;
-          for (int kb = 0; kb < kblocks; ++kb, ++it) {
-            const uint32_t stage = it % Cfg::STAGES;
-            const uint32_t phase = (it / Cfg::STAGES) & 1;
-            mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const TileCoord t = decode_tile<BM>(p, tile);
+      const int dil = p.dil[t.g];
+      for (int s = 0; s < p.num_segs; ++s) {
+        const ns2_gemm_seg sg = p.segs[s];
+        const int row0 = t.n0 - sg.shift_units * dil;
+        const int a_c0 = t.g * p.a_gcs + sg.a_col_off;
+        const int b_r0 = t.g * p.b_grs + t.n_tile * BN;
+        const int kblocks = (sg.k_len + BK - 1) / BK;
+        for (int kb = 0; kb < kblocks; ++kb, ++it) {
+          const uint32_t stage = it % Cfg::STAGES;
+          const uint32_t phase = (it / Cfg::STAGES) & 1;
+          mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+          if (elect_one()) {
             const uint32_t fb = smem_u32(&full_bar[stage]);
             mbar_arrive_expect_tx(fb, Cfg::STAGE_BYTES);
             uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
             tma_load_3d(smem_u32(sa), &p.tmA, fb, a_c0 + kb * BK, row0, t.b);
             tma_load_2d(smem_u32(sa + Cfg::A_BYTES), &p.tmB, fb, sg.b_col_off + kb * BK, b_r0);
           }
+          __syncwarp();
         }
       }
     }
   } else if (warp == 1) {
     // =============================== MMA issuer =================================
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_f16(BM, BN, /*bf16*/ 1, 0, 0);
-      uint32_t it = 0;
-      uint32_t ti = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++ti) {
-        const uint32_t as = ti & 1;
-        const uint32_t aphase = (ti >> 1) & 1;
-        mbar_wait(smem_u32(&tempty_bar[as]), aphase ^ 1);
-        tc_fence_after();
-        uint32_t started = 0;  // bit a set once accumulator a has received its first MMA
-        for (int s = 0; s < p.num_segs; ++s) {
-          const int acc = p.segs[s].acc;
-          const uint32_t d_tmem = tmem_base + as * Cfg::ACC_COLS + acc * BN;
-          const int kblocks = (p.segs[s].k_len + BK - 1) / BK;
-          for (int kb = 0; kb < kblocks; ++kb, ++it) {
-            const uint32_t stage = it % Cfg::STAGES;
-            const uint32_t phase = (it / Cfg::STAGES) & 1;
-            mbar_wait(smem_u32(&full_bar[stage]), phase);
-            tc_fence_after();
-            const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
-            const uint64_t da = umma_desc_sw128(sa, 16, 1024);
-            const uint64_t db = umma_desc_sw128(sa + Cfg::A_BYTES, 16, 1024);
+    constexpr uint32_t idesc = umma_idesc_f16(BM, BN, /*bf16*/ 1, 0, 0);
+    uint32_t it = 0;
+    uint32_t ti = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++ti) {
+      const uint32_t as = ti & 1;
+      const uint32_t aphase = (ti >> 1) & 1;
+      mbar_wait(smem_u32(&tempty_bar[as]), aphase ^ 1);
+      tc_fence_after();
+      uint32_t started = 0;  // bit a set once accumulator a has received its first MMA
+      for (int s = 0; s < p.num_segs; ++s) {
+        const int acc = p.segs[s].acc;
+        const uint32_t d_tmem = tmem_base + as * Cfg::ACC_COLS + acc * BN;
+        const int kblocks = (p.segs[s].k_len + BK - 1) / BK;
+        for (int kb = 0; kb < kblocks; ++kb, ++it) {
+          const uint32_t stage = it % Cfg::STAGES;
+          const uint32_t phase = (it / Cfg::STAGES) & 1;
+          mbar_wait(smem_u32(&full_bar[stage]), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint64_t da = umma_desc_sw128(sa, 16, 1024);
+          const uint64_t db = umma_desc_sw128(sa + Cfg::A_BYTES, 16, 1024);
+          if (elect_one()) {
 #pragma unroll
             for (int k = 0; k < BK / 16; ++k) {
               // advancing 16 elements (32 bytes) along K inside the 128-byte swizzle atom
               tc_mma_f16(d_tmem, da + 2 * k, db + 2 * k, idesc, ((started >> acc) & 1) | (k > 0));
             }
-            started |= 1u << acc;
             tc_commit(smem_u32(&empty_bar[stage]));  // frees the smem slot when these MMAs retire
           }
+          __syncwarp();
+          started |= 1u << acc;
         }
-        tc_commit(smem_u32(&tfull_bar[as]));  // accumulators of this tile complete
       }
+      if (elect_one()) tc_commit(smem_u32(&tfull_bar[as]));  // accumulators of this tile complete
+      __syncwarp();
     }
   } else if (warp >= 4) {
     // =============================== epilogue ===================================
@@ -603,26 +598,24 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
   const uint32_t tmem_base = *tmem_holder;
 
   if (warp == 0) {
-    // =============================== TMA producer (both CTAs) ===================
-    if (lane == 0) {
-      uint32_t it = 0;
-      uint32_t ti = 0;
-      for (int tile = pair; tile < p.num_tiles; tile += num_pairs, ++ti) {
-        const TileCoord t = decode_tile<2 * BM>(p, tile);
-        const int dil = p.dil[t.g];
-        NS2_DBG_STAMP(4);
-        for (int s = 0; s < p.num_segs; ++s) {
-          const ns2_gemm_seg sg = p.segs[s];
-          const int row0 = t.n0 + static_cast<int>(rank) * BM - sg.shift_units * dil;
-          const int a_c0 = t.g * p.a_gcs + sg.a_col_off;
-          // a partial last n-tile is computed with N = bn_eff: each CTA then supplies bn_eff/2 B rows
-          const int bn_eff = (p.n - t.n_tile * BN) < BN ? (p.n - t.n_tile * BN) : BN;
-          const int b_r0 = t.g * p.b_grs + t.n_tile * BN + static_cast<int>(rank) * (bn_eff / 2);
-          const int kblocks = (sg.k_len + BK - 1) / BK;
-          for (int kb = 0; kb < kblocks; ++kb, ++it) {
-            const uint32_t stage = it % Cfg::STAGES;
-            const uint32_t phase = (it / Cfg::STAGES) & 1;
-            mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+    // =============================== TMA producer (both CTAs; converged, see gemm_kernel) ===================
+    uint32_t it = 0;
+    for (int tile = pair; tile < p.num_tiles; tile += num_pairs) {
+      const TileCoord t = decode_tile<2 * BM>(p, tile);
+      const int dil = p.dil[t.g];
+      // a partial last n-tile is computed with N = bn_eff: each CTA then supplies bn_eff/2 B rows
+      const int bn_eff = (p.n - t.n_tile * BN) < BN ? (p.n - t.n_tile * BN) : BN;
+      const int b_r0 = t.g * p.b_grs + t.n_tile * BN + static_cast<int>(rank) * (bn_eff / 2);
+      for (int s = 0; s < p.num_segs; ++s) {
+        const ns2_gemm_seg sg = p.segs[s];
+        const int row0 = t.n0 + static_cast<int>(rank) * BM - sg.shift_units * dil;
+        const int a_c0 = t.g * p.a_gcs + sg.a_col_off;
+        const int kblocks = (sg.k_len + BK - 1) / BK;
+        for (int kb = 0; kb < kblocks; ++kb, ++it) {
+          const uint32_t stage = it % Cfg::STAGES;
+          const uint32_t phase = (it / Cfg::STAGES) & 1;
+          mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+          if (elect_one()) {
             // the transaction bytes of both CTAs are counted on the leader's barrier
             const uint32_t fb_leader = mapa_shared(smem_u32(&full_bar[stage]), 0);
             if (leader) mbar_arrive_expect_tx(smem_u32(&full_bar[stage]), 2 * Cfg::STAGE_BYTES);
@@ -630,13 +623,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
             tma_load_3d_2sm(smem_u32(sa), &p.tmA, fb_leader, a_c0 + kb * BK, row0, t.b);
             tma_load_2d_2sm(smem_u32(sa + Cfg::A_BYTES), &p.tmB, fb_leader, sg.b_col_off + kb * BK, b_r0);
           }
+          __syncwarp();
         }
-        NS2_DBG_STAMP(5);
       }
     }
   } else if (warp == 1) {
-    // =============================== MMA issuer (leader CTA only) ================
-    if (leader && lane == 0) {
+    // =============================== MMA issuer (leader CTA only; converged) ================
+    if (leader) {
       uint32_t it = 0;
       uint32_t ti = 0;
       for (int tile = pair; tile < p.num_tiles; tile += num_pairs, ++ti) {
@@ -645,10 +638,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
         const uint32_t idesc = umma_idesc_f16(2 * BM, bn_eff, /*bf16*/ 1, 0, 0);
         const uint32_t as = (Cfg::ACC_STAGES == 2) ? (ti & 1) : 0;
         const uint32_t aphase = (Cfg::ACC_STAGES == 2) ? ((ti >> 1) & 1) : (ti & 1);
-        NS2_DBG_STAMP(0);
         mbar_wait(smem_u32(&tempty_bar[as]), aphase ^ 1);
         tc_fence_after();
-        NS2_DBG_STAMP(1);
         uint32_t started = 0;
         for (int s = 0; s < p.num_segs; ++s) {
           const int acc = p.segs[s].acc;
@@ -659,19 +650,21 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
             const uint32_t phase = (it / Cfg::STAGES) & 1;
             mbar_wait(smem_u32(&full_bar[stage]), phase);
             tc_fence_after();
-            if (s == 0 && kb == 0) NS2_DBG_STAMP(2);
             const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
             const uint64_t da = umma_desc_sw128(sa, 16, 1024);
             const uint64_t db = umma_desc_sw128(sa + Cfg::A_BYTES, 16, 1024);
+            if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < BK / 16; ++k)
-              tc_mma_f16_2cta(d_tmem, da + 2 * k, db + 2 * k, idesc, ((started >> acc) & 1) | (k > 0));
+              for (int k = 0; k < BK / 16; ++k)
+                tc_mma_f16_2cta(d_tmem, da + 2 * k, db + 2 * k, idesc, ((started >> acc) & 1) | (k > 0));
+              tc_commit_2cta(smem_u32(&empty_bar[stage]), 0b11);  // frees the slot in both CTAs
+            }
+            __syncwarp();
             started |= 1u << acc;
-            tc_commit_2cta(smem_u32(&empty_bar[stage]), 0b11);  // frees the slot in both CTAs
           }
         }
-        tc_commit_2cta(smem_u32(&tfull_bar[as]), 0b11);  // both CTAs' epilogues may read their 128 rows
-        NS2_DBG_STAMP(3);
+        if (elect_one()) tc_commit_2cta(smem_u32(&tfull_bar[as]), 0b11);  // both CTAs' epilogues may read their rows
+        __syncwarp();
       }
     }
   } else if (warp >= 4) {
@@ -686,20 +679,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
       const TileCoord t = decode_tile<2 * BM>(p, tile);
       const uint32_t as = (Cfg::ACC_STAGES == 2) ? (ti & 1) : 0;
       const uint32_t aphase = (Cfg::ACC_STAGES == 2) ? ((ti >> 1) & 1) : (ti & 1);
-      if (ew == 0 && lane == 0) NS2_DBG_STAMP(6);
       mbar_wait(smem_u32(&tfull_bar[as]), aphase);
       tc_fence_after();
-      if (ew == 0 && lane == 0) NS2_DBG_STAMP(7);
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + as * Cfg::ACC_STRIDE;
-      if (!(p.debug & 4))
+      if (!p.skip_epilogue)
         epilogue_tile_tma<BN, NACC, EPI>(p, t, taddr, t.n0 + static_cast<int>(rank) * BM + ew * 32, st);
       // all TMEM reads of this tile are complete: hand the accumulator stage back to the leader's MMA warp
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(&tempty_bar[as]), 0));
-      if (ew == 0 && lane == 0) NS2_DBG_STAMP(8);
     }
-    if (lane == 0) tma_store_wait_all();  // staging smem must outlive the bulk stores that read it
+    if (elect_one()) tma_store_wait_all();  // staging smem must outlive the bulk stores that read it
+    __syncwarp();
   }
 
   // neither CTA may free TMEM / exit while its peer can still touch it (MMA writes, remote barrier arrives)
@@ -741,13 +732,6 @@ static int launch_gemm2(const GemmDev& dev, cudaStream_t stream) {
 }
 
 }  // namespace ns2
-
-extern "C" int ns2_debug_gemm_timeline(long long* dst_host, int n) {
-  // bring-up aid (not part of the public header): copy the clock64 stamps recorded under NS2_GEMM_DEBUG=8
-  if (n > 16 * 64) n = 16 * 64;
-  cudaError_t e = cudaMemcpyFromSymbol(dst_host, ns2::g_gemm_dbg, sizeof(long long) * n);
-  return e == cudaSuccess ? 0 : -2;
-}
 
 extern "C" int ns2_gemm(const ns2_gemm_args* a, ns2_stream_t stream_) {
   using namespace ns2;
@@ -858,10 +842,7 @@ extern "C" int ns2_gemm(const ns2_gemm_args* a, ns2_stream_t stream_) {
   dev.film = a->film;
   dev.film_bs = a->film_batch_stride;
   dev.film_gs = a->film_group_stride;
-  {
-    const char* dbg = getenv("NS2_GEMM_DEBUG");
-    dev.debug = dbg ? atoi(dbg) : 0;
-  }
+  dev.skip_epilogue = (a->flags & NS2_GEMM_FLAG_SKIP_EPILOGUE) ? 1 : 0;
 
   if (pair) {
     switch (a->epilogue) {

@@ -14,6 +14,10 @@ dev = "cuda"
 bf = torch.bfloat16
 which = set(sys.argv[1:]) or {"conv", "attn", "wavenet", "ffin", "ffout", "qkv", "norm", "rvq"}
 reps = 3
+import os  # noqa: E402
+FLAGS = int(os.environ.get("NS2_GEMM_FLAGS", "0"))   # 1 = mainloop only (NS2_GEMM_FLAG_SKIP_EPILOGUE)
+_gemm = ops.gemm
+ops.gemm = lambda *a, **k: _gemm(*a, flags=FLAGS, **k)
 
 
 def timeit(name, fn, flops=None, bytes_=None):

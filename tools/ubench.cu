@@ -176,6 +176,61 @@ __global__ void alu_kernel(long long* out, float* sink, int iters, float seed) {
   if ((threadIdx.x & 31) == 0) out[warp] = t1 - t0;
 }
 
+// the softmax inner loop of the attention kernel in isolation: 128 values per thread,
+//   x = fma2(s, c, -m) -> ex2 -> sum (add2) -> pack to bf16 pairs
+// PACK: 0 = cvt.rn.bf16x2 (F2FP), 1 = integer round + PRMT, 2 = no packing (sum only)
+template <int PACK>
+__global__ void softmax_loop_kernel(long long* out, float* sink, int iters, float seed) {
+  const int warp = threadIdx.x >> 5;
+  float s[128];
+#pragma unroll
+  for (int i = 0; i < 128; ++i) s[i] = seed * (i + 1) - 0.01f * threadIdx.x;
+  float acc = 0.f;
+  uint32_t iacc = 0;
+  unsigned long long c2, nm2;
+  asm("mov.b64 %0, {%1,%1};" : "=l"(c2) : "f"(0.18f));
+  __syncthreads();
+  const long long t0 = clock64();
+  for (int it = 0; it < iters; ++it) {
+    asm("mov.b64 %0, {%1,%1};" : "=l"(nm2) : "f"(-1.0f - 1e-3f * it));
+    unsigned long long l0 = 0ull, l1 = 0ull;
+#pragma unroll
+    for (int i = 0; i < 128; i += 4) {
+      unsigned long long x0, x1;
+      asm("mov.b64 %0, {%1,%2};" : "=l"(x0) : "f"(s[i]), "f"(s[i + 1]));
+      asm("mov.b64 %0, {%1,%2};" : "=l"(x1) : "f"(s[i + 2]), "f"(s[i + 3]));
+      asm volatile("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(x0) : "l"(x0), "l"(c2), "l"(nm2));
+      asm volatile("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(x1) : "l"(x1), "l"(c2), "l"(nm2));
+      float a0, a1, a2, a3;
+      asm("mov.b64 {%0,%1}, %2;" : "=f"(a0), "=f"(a1) : "l"(x0));
+      asm("mov.b64 {%0,%1}, %2;" : "=f"(a2), "=f"(a3) : "l"(x1));
+      a0 = ex2a(a0); a1 = ex2a(a1); a2 = ex2a(a2); a3 = ex2a(a3);
+      unsigned long long e0, e1;
+      asm("mov.b64 %0, {%1,%2};" : "=l"(e0) : "f"(a0), "f"(a1));
+      asm("mov.b64 %0, {%1,%2};" : "=l"(e1) : "f"(a2), "f"(a3));
+      asm volatile("add.rn.f32x2 %0, %1, %2;" : "=l"(l0) : "l"(l0), "l"(e0));
+      asm volatile("add.rn.f32x2 %0, %1, %2;" : "=l"(l1) : "l"(l1), "l"(e1));
+      if constexpr (PACK == 0) {
+        uint32_t p0, p1;
+        asm volatile("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(p0) : "f"(a1), "f"(a0));
+        asm volatile("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(p1) : "f"(a3), "f"(a2));
+        iacc ^= p0 + p1;
+      } else if constexpr (PACK == 1) {
+        const uint32_t p0 = __byte_perm(__float_as_uint(a0) + 0x8000u, __float_as_uint(a1) + 0x8000u, 0x7632);
+        const uint32_t p1 = __byte_perm(__float_as_uint(a2) + 0x8000u, __float_as_uint(a3) + 0x8000u, 0x7632);
+        iacc ^= p0 + p1;
+      }
+    }
+    float q0, q1, q2, q3;
+    asm("mov.b64 {%0,%1}, %2;" : "=f"(q0), "=f"(q1) : "l"(l0));
+    asm("mov.b64 {%0,%1}, %2;" : "=f"(q2), "=f"(q3) : "l"(l1));
+    acc += q0 + q1 + q2 + q3;
+  }
+  const long long t1 = clock64();
+  sink[threadIdx.x] = acc + __uint_as_float(iacc);
+  if ((threadIdx.x & 31) == 0) out[warp] = t1 - t0;
+}
+
 static long long maxof(const std::vector<long long>& v, int n) {
   long long m = 0;
   for (int i = 0; i < n; ++i) m = v[i] > m ? v[i] : m;
@@ -227,6 +282,24 @@ int main() {
       const double cyc = (double)maxof(h, warps);
       printf("%-28s warps=%2d  cycles/iter=%8.1f  (per SMSP-warp-slot: %6.1f)\n", an[mode], warps, cyc / iters,
              cyc / iters / ((warps + 3) / 4));
+    }
+  }
+  const char* sn[3] = {"softmax loop 128 elems (F2FP pack)", "softmax loop 128 elems (int pack)",
+                       "softmax loop 128 elems (no pack)"};
+  for (int mode = 0; mode < 3; ++mode) {
+    for (int warps : {4, 8, 12}) {
+      for (int rep = 0; rep < 2; ++rep) {
+        float* fs = reinterpret_cast<float*>(d_sink);
+        if (mode == 0) softmax_loop_kernel<0><<<1, warps * 32>>>(d_out, fs, iters, 0.01f);
+        if (mode == 1) softmax_loop_kernel<1><<<1, warps * 32>>>(d_out, fs, iters, 0.01f);
+        if (mode == 2) softmax_loop_kernel<2><<<1, warps * 32>>>(d_out, fs, iters, 0.01f);
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) { printf("error: %s\n", cudaGetErrorString(e)); return 1; }
+      }
+      cudaMemcpy(h.data(), d_out, 64 * sizeof(long long), cudaMemcpyDeviceToHost);
+      const double cyc = (double)maxof(h, warps);
+      printf("%-36s warps=%2d  cycles/iter=%8.1f  (per warp on an SMSP: %7.1f, per element-warp %5.2f)\n", sn[mode],
+             warps, cyc / iters, cyc / iters / ((warps + 3) / 4), cyc / iters / ((warps + 3) / 4) / 128.0);
     }
   }
   return 0;
