@@ -176,10 +176,12 @@ def import_reference():
     stub("num_to_words", num_to_word=lambda *a, **k: "")
     if str(ref_dir) not in sys.path:
         sys.path.insert(0, str(ref_dir))
+    import contextlib
     import warnings
     warnings.filterwarnings("ignore", category=FutureWarning)
     try:
-        from naturalspeech2_pytorch import naturalspeech2_pytorch as ns2
+        with contextlib.redirect_stdout(sys.stderr):   # the reference prints at import / first call; stdout = JSON only
+            from naturalspeech2_pytorch import naturalspeech2_pytorch as ns2
     except Exception as e:  # missing dependency on this box
         print(f"bench: reference import failed ({type(e).__name__}: {e}); using the oracle port", file=sys.stderr)
         return None
@@ -211,8 +213,9 @@ class HostReference:
             self.desc = "torch fp32 CPU port of the reference path (oracle/denoiser_torch_port.py)"
 
     def forward(self, x, t, autocast_bf16=False):
+        import contextlib
         import torch
-        with torch.no_grad():
+        with torch.no_grad(), contextlib.redirect_stdout(sys.stderr):
             if self.kind == "reference":
                 if autocast_bf16:
                     with torch.autocast("cpu", dtype=torch.bfloat16):

@@ -383,6 +383,110 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmDev& p, const TileCo
 }
 
 // ------------------------------------------------------------------------------------------------
+// pair-kernel epilogue, 8 warps per CTA: warp e (0..7) owns TMEM lane quarter e & 3 (32 positions) and column half
+// e >> 2 of the tile, so every SM sub-partition has two epilogue warps to hide each other's TMEM / shared-memory
+// latencies.  Inside a warp the 32-column steps are software-pipelined: the tcgen05.ld of step s+1 is in flight while
+// step s is being computed and staged.  registers -> 128B-swizzled smem staging (per warp, double-buffered) -> TMA.
+// ------------------------------------------------------------------------------------------------
+// taddr: TMEM address (first lane of this warp's quarter, first column of the accumulator stage); row0: first position
+// of this warp's 32 rows; hsel: column half.  Returns after the last TMEM read of the tile (stores may be in flight).
+template <int BN, int NACC, int EPI>
+__device__ __forceinline__ void epilogue_tile_tma8(const GemmDev& p, const TileCoord& t, uint32_t taddr, int row0,
+                                                   int hsel, Stager& st) {
+  const int tile_col0 = t.n_tile * BN;
+  constexpr bool kTwo = (EPI == NS2_EPI_GEGLU || EPI == NS2_EPI_WAVENET);   // two accumulator regions per step
+  constexpr int HALF = (EPI == NS2_EPI_GEGLU) ? 64 : BN / 2;                // output columns of this warp per tile
+  constexpr int STEPS = HALF / 32;
+  const int c_base = hsel * HALF;                                           // first (value) column of this warp
+  constexpr int SECOND = (EPI == NS2_EPI_GEGLU) ? 128 : BN;                 // column offset of the second region
+  // steps whose columns lie inside the matrix (n is a multiple of 32; a partial last n-tile is narrower)
+  int nsteps = 0;
+#pragma unroll
+  for (int s = 0; s < STEPS; ++s)
+    if (tile_col0 + ((EPI == NS2_EPI_GEGLU) ? 0 : c_base + s * 32) < p.n) nsteps = s + 1;
+  if (nsteps == 0) return;
+
+  uint32_t ra[2][32], rb[2][32];
+  auto load = [&](int s, int buf) {
+    tmem_ld32(taddr + c_base + s * 32, ra[buf]);
+    if constexpr (kTwo) tmem_ld32(taddr + SECOND + c_base + s * 32, rb[buf]);
+  };
+  load(0, 0);
+  uint32_t box = 0;
+#pragma unroll
+  for (int s = 0; s < STEPS; ++s) {
+    if (s < nsteps) {
+      const int buf = s & 1;
+      tmem_ld_wait();
+      if (s + 1 < STEPS && s + 1 < nsteps) load(s + 1, buf ^ 1);   // in flight during this step's math
+      const int c = c_base + s * 32;                               // tile column of this step
+      float v[32];
+      if constexpr (EPI == NS2_EPI_BF16 || EPI == NS2_EPI_F32) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(ra[buf][i]);
+        if (p.bias != nullptr) add_vec<32>(v, p.bias + t.g * p.b_grs + tile_col0 + c);
+      } else if constexpr (EPI == NS2_EPI_GEGLU) {
+        const float4* bv4 = reinterpret_cast<const float4*>(p.bias + t.g * p.b_grs + tile_col0 + c);
+        const float4* bg4 = bv4 + 32;   // gate bias: + 128 columns
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {   // 4 columns at a time: keeps the bias temporaries out of the register peak
+          const float4 bv = __ldg(bv4 + q), bg = __ldg(bg4 + q);
+          const float bva[4] = {bv.x, bv.y, bv.z, bv.w}, bga[4] = {bg.x, bg.y, bg.z, bg.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int i = 4 * q + j;
+            v[i] = (__uint_as_float(ra[buf][i]) + bva[j]) * gelu_erf_fast(__uint_as_float(rb[buf][i]) + bga[j]);
+          }
+        }
+      } else {  // NS2_EPI_WAVENET: y = tanh(z) sigmoid(z) + res, z = conv * gamma + beta   (ns2.py:619-636)
+        const int col0 = tile_col0 + c;
+        const float4* b04 = reinterpret_cast<const float4*>(p.bias + t.g * p.b_grs + col0);
+        const float4* b14 = reinterpret_cast<const float4*>(p.bias + t.g * p.b_grs + col0 + p.bias1_off);
+        const float4* ga4 = reinterpret_cast<const float4*>(p.film + t.b * p.film_bs + t.g * p.film_gs + col0);
+        const float4* be4 = reinterpret_cast<const float4*>(p.film + t.b * p.film_bs + t.g * p.film_gs + col0 + p.n);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 b0 = __ldg(b04 + q), b1 = __ldg(b14 + q), g4 = __ldg(ga4 + q), e4 = __ldg(be4 + q);
+          const float b0a[4] = {b0.x, b0.y, b0.z, b0.w}, b1a[4] = {b1.x, b1.y, b1.z, b1.w};
+          const float gaa[4] = {g4.x, g4.y, g4.z, g4.w}, bea[4] = {e4.x, e4.y, e4.z, e4.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int i = 4 * q + j;
+            const float z = fmaf(__uint_as_float(ra[buf][i]) + b0a[j], gaa[j], bea[j]);
+            // tanh(z) * sigmoid(z) with ONE MUFU: u = tanh(z/2); sigmoid = (1 + u)/2; tanh(z) = 2u / (1 + u^2), the
+            // reciprocal of w = 1 + u^2 in [1, 2] by a linear seed + two Newton steps on the FMA pipe (rel. err < 2e-5)
+            const float u = tanh_fast(0.5f * z);
+            const float w = fmaf(u, u, 1.0f);
+            float r = fmaf(-0.47058824f, w, 1.4117647f);     // 24/17 - 8/17 w: |1 - w r| <= 1/17 on [1, 2]
+            r = r * fmaf(-w, r, 2.0f);
+            r = r * fmaf(-w, r, 2.0f);
+            const float gate = (u * r) * (1.0f + u);          // = tanh(z) * sigmoid(z)
+            v[i] = gate + (__uint_as_float(rb[buf][i]) + b1a[j]);
+          }
+        }
+      }
+      // ---- stage + store ----
+      if constexpr (EPI == NS2_EPI_F32) {
+        box = st.acquire();
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          st.put(box, q, make_uint4(__float_as_uint(v[4 * q]), __float_as_uint(v[4 * q + 1]),
+                                    __float_as_uint(v[4 * q + 2]), __float_as_uint(v[4 * q + 3])));
+        st.submit(&p.tmOut, box, t.g * p.out_gcs + tile_col0 + c, row0, t.b, p.reduce_add != 0);
+      } else {
+        if ((s & 1) == 0) box = st.acquire();
+        put_bf16x32(st, box, s & 1, v);
+        if ((s & 1) == 1 || s + 1 == nsteps) {
+          const int oc = c - (s & 1) * 32;   // first output column of the 64-column box
+          const int out_col = (EPI == NS2_EPI_GEGLU) ? t.n_tile * 128 + oc : tile_col0 + oc;
+          st.submit(&p.tmOut, box, t.g * p.out_gcs + out_col, row0, t.b, false);
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // single-CTA kernel
 // ------------------------------------------------------------------------------------------------
 template <int BN, int NACC>
@@ -537,8 +641,10 @@ struct Gemm2Cfg {
   static constexpr int A_BYTES = BM * BK * 2;            // this CTA's 128 rows
   static constexpr int B_BYTES = (BN / 2) * BK * 2;      // this CTA's half of the B tile
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;  // multiple of 1024 for BN in {128, 176, 256}
-  static constexpr int STG_TOTAL = 4 * 2 * STG_BYTES;    // 4 epilogue warps x 2 staging boxes
-  static constexpr int STAGES = (192 * 1024) / STAGE_BYTES > 8 ? 8 : (192 * 1024) / STAGE_BYTES;
+  static constexpr int EPI_WARPS = 8;                    // two per SM sub-partition (lane quarter x column half)
+  static constexpr int THREADS = (4 + EPI_WARPS) * 32;
+  static constexpr int STG_TOTAL = EPI_WARPS * 2 * STG_BYTES;   // 2 staging boxes per epilogue warp
+  static constexpr int STAGES = (160 * 1024) / STAGE_BYTES > 8 ? 8 : (160 * 1024) / STAGE_BYTES;
   static constexpr int ACC_COLS = BN * NACC;
   // accumulators are double-buffered across tiles when two sets fit the 512 TMEM columns; the 256-wide two-accumulator
   // (wavenet) tile uses all 512 columns, so its epilogue and the next tile's MMAs take turns
@@ -553,7 +659,7 @@ struct Gemm2Cfg {
 };
 
 template <int BN, int NACC, int EPI>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Gemm2Cfg<BN, NACC>::THREADS, 1)
     gemm2_kernel(const __grid_constant__ GemmDev p) {
   using Cfg = Gemm2Cfg<BN, NACC>;
   extern __shared__ uint8_t smem_raw[];
@@ -564,7 +670,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
   uint64_t* full_bar = bars;                          // [STAGES]  used in the leader CTA only
   uint64_t* empty_bar = bars + Cfg::STAGES;           // [STAGES]  one per CTA, signalled by multicast commit
   uint64_t* tfull_bar = bars + 2 * Cfg::STAGES;       // [2]       one per CTA, multicast commit
-  uint64_t* tempty_bar = bars + 2 * Cfg::STAGES + 2;  // [2]       leader only: 8 arrivals (4 warps x 2 CTAs)
+  uint64_t* tempty_bar = bars + 2 * Cfg::STAGES + 2;  // [2]       leader only: 16 arrivals (8 warps x 2 CTAs)
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::STAGES + 4);
 
   const int warp = threadIdx.x >> 5;
@@ -586,7 +692,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(smem_u32(&tfull_bar[i]), 1);
-      mbar_init(smem_u32(&tempty_bar[i]), 8);
+      mbar_init(smem_u32(&tempty_bar[i]), 2 * Cfg::EPI_WARPS);
     }
     fence_barrier_init();
   }
@@ -597,6 +703,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
 
+  // register budget (setmaxnreg): the service warpgroup (TMA, MMA, TMEM allocator, one idle warp) gives registers to the
+  // two epilogue warpgroups, whose software-pipelined steps hold two sets of accumulator fragments
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
   if (warp == 0) {
     // =============================== TMA producer (both CTAs; converged, see gemm_kernel) ===================
     uint32_t it = 0;
@@ -667,9 +777,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
         __syncwarp();
       }
     }
-  } else if (warp >= 4) {
-    // =============================== epilogue (both CTAs) =======================
+  }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
+    // =============================== epilogue (both CTAs, 8 warps each) =======================
     const int ew = warp - 4;
+    const int quarter = ew & 3;   // == warp % 4: the TMEM lane quarter this warp may read
+    const int hsel = ew >> 2;     // column half of the tile
     Stager st;
     st.base = smem_u32(smem + Cfg::OFF_STG + ew * 2 * STG_BYTES);
     st.count = 0;
@@ -681,9 +795,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
       const uint32_t aphase = (Cfg::ACC_STAGES == 2) ? ((ti >> 1) & 1) : (ti & 1);
       mbar_wait(smem_u32(&tfull_bar[as]), aphase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + as * Cfg::ACC_STRIDE;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * Cfg::ACC_STRIDE;
       if (!p.skip_epilogue)
-        epilogue_tile_tma<BN, NACC, EPI>(p, t, taddr, t.n0 + static_cast<int>(rank) * BM + ew * 32, st);
+        epilogue_tile_tma8<BN, NACC, EPI>(p, t, taddr, t.n0 + static_cast<int>(rank) * BM + quarter * 32, hsel, st);
       // all TMEM reads of this tile are complete: hand the accumulator stage back to the leader's MMA warp
       tc_fence_before();
       __syncwarp();
@@ -725,7 +839,7 @@ static int launch_gemm2(const GemmDev& dev, cudaStream_t stream) {
   NS2_CUDA_CHECK(set_max_smem_once(kern, Cfg::SMEM_BYTES));
   int pairs = num_sms() / 2;
   if (dev.num_tiles < pairs) pairs = dev.num_tiles;
-  kern<<<2 * pairs, 256, Cfg::SMEM_BYTES, stream>>>(dev);  // __cluster_dims__(2,1,1)
+  kern<<<2 * pairs, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(dev);  // __cluster_dims__(2,1,1)
   g_launches.fetch_add(1, std::memory_order_relaxed);
   NS2_CUDA_CHECK(cudaGetLastError());
   return kOk;
