@@ -92,6 +92,8 @@ typedef struct ns2_gemm_args {
   int64_t film_batch_stride;
   int32_t film_group_stride;
   int32_t flags;           /* 0, or NS2_GEMM_FLAG_* */
+  void* debug_timeline;    /* bring-up aid, normally NULL: device buffer of 64*8 int64 receiving clock64 stamps of CTA
+                              pair 0 of the CTA-pair kernel (tools/gemm_timeline.py) */
 } ns2_gemm_args;
 
 #define NS2_GEMM_FLAG_SKIP_EPILOGUE 1  /* measurement aid: run the TMA/MMA mainloop only, write nothing (CTA-pair kernel) */

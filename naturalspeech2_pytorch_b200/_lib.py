@@ -37,7 +37,7 @@ class GemmArgs(C.Structure):
         ("out", C.c_void_p), ("out_row_stride", C.c_int64),
         ("resid", C.c_void_p), ("resid_row_stride", C.c_int64),
         ("film", C.c_void_p), ("film_batch_stride", C.c_int64), ("film_group_stride", C.c_int32),
-        ("flags", C.c_int32),
+        ("flags", C.c_int32), ("debug_timeline", C.c_void_p),
     ]
 
 

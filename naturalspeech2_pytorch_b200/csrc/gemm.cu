@@ -52,7 +52,14 @@ struct GemmDev {
   long long film_bs;
   int film_gs;
   int skip_epilogue;  // measurement aid (ns2_gemm_args.flags & NS2_GEMM_FLAG_SKIP_EPILOGUE): mainloop-only timing
+  long long* timeline;  // bring-up aid (ns2_gemm_args.debug_timeline): clock64 stamps of CTA pair 0, else NULL
 };
+
+// timeline layout: [tile ti < 64][8 slots] of the leader CTA of pair 0 (tools/gemm_timeline.py)
+#define NS2_GEMM_STAMP(slot)                                                                             \
+  do {                                                                                                   \
+    if (p.timeline != nullptr && pair == 0 && leader && ti < 64) p.timeline[ti * 8 + (slot)] = clock64(); \
+  } while (0)
 
 struct TileCoord {
   int g, b, n0, n_tile;
@@ -748,8 +755,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Gemm2Cfg<BN, NACC>::
         const uint32_t idesc = umma_idesc_f16(2 * BM, bn_eff, /*bf16*/ 1, 0, 0);
         const uint32_t as = (Cfg::ACC_STAGES == 2) ? (ti & 1) : 0;
         const uint32_t aphase = (Cfg::ACC_STAGES == 2) ? ((ti >> 1) & 1) : (ti & 1);
+        if (lane == 0) NS2_GEMM_STAMP(0);
         mbar_wait(smem_u32(&tempty_bar[as]), aphase ^ 1);
         tc_fence_after();
+        if (lane == 0) NS2_GEMM_STAMP(1);
         uint32_t started = 0;
         for (int s = 0; s < p.num_segs; ++s) {
           const int acc = p.segs[s].acc;
@@ -775,6 +784,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Gemm2Cfg<BN, NACC>::
         }
         if (elect_one()) tc_commit_2cta(smem_u32(&tfull_bar[as]), 0b11);  // both CTAs' epilogues may read their rows
         __syncwarp();
+        if (lane == 0) NS2_GEMM_STAMP(2);
       }
     }
   }
@@ -793,8 +803,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Gemm2Cfg<BN, NACC>::
       const TileCoord t = decode_tile<2 * BM>(p, tile);
       const uint32_t as = (Cfg::ACC_STAGES == 2) ? (ti & 1) : 0;
       const uint32_t aphase = (Cfg::ACC_STAGES == 2) ? ((ti >> 1) & 1) : (ti & 1);
+      if (ew == 0 && lane == 0) NS2_GEMM_STAMP(3);
+      if (ew == 7 && lane == 0) NS2_GEMM_STAMP(6);
       mbar_wait(smem_u32(&tfull_bar[as]), aphase);
       tc_fence_after();
+      if (ew == 0 && lane == 0) NS2_GEMM_STAMP(4);
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * Cfg::ACC_STRIDE;
       if (!p.skip_epilogue)
         epilogue_tile_tma8<BN, NACC, EPI>(p, t, taddr, t.n0 + static_cast<int>(rank) * BM + quarter * 32, hsel, st);
@@ -802,6 +815,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Gemm2Cfg<BN, NACC>::
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(&tempty_bar[as]), 0));
+      if (ew == 0 && lane == 0) NS2_GEMM_STAMP(5);
+      if (ew == 7 && lane == 0) NS2_GEMM_STAMP(7);
     }
     if (elect_one()) tma_store_wait_all();  // staging smem must outlive the bulk stores that read it
     __syncwarp();
@@ -957,6 +972,7 @@ extern "C" int ns2_gemm(const ns2_gemm_args* a, ns2_stream_t stream_) {
   dev.film_bs = a->film_batch_stride;
   dev.film_gs = a->film_group_stride;
   dev.skip_epilogue = (a->flags & NS2_GEMM_FLAG_SKIP_EPILOGUE) ? 1 : 0;
+  dev.timeline = reinterpret_cast<long long*>(a->debug_timeline);
 
   if (pair) {
     switch (a->epilogue) {

@@ -243,9 +243,12 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t local_addr, uint32_t ra
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
   return r;
 }
+// Arrive on an mbarrier of another CTA of the cluster.  Default semantics (.release at .cta scope): an explicit
+// `.release.cluster` makes ptxas emit MEMBAR.ALL.GPU + ERRBAR in front of every arrive (~1-2k cycles per tile in the GEMM
+// epilogue, profiles/r02_gemm_timeline.txt); what the consumer needs ordered here are tcgen05 (TMEM) accesses, which the
+// tcgen05.fence::before_thread_sync issued by the caller covers.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr)
-               : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA loads issued by either CTA of a pair: data lands in the issuing CTA's smem, the transaction bytes are
 // reported to `bar_cluster`, an mbarrier that may live in the peer (leader) CTA.

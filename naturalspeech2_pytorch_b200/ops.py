@@ -54,7 +54,8 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, n: int, epilogu
          resid: Optional[torch.Tensor] = None, film: Optional[torch.Tensor] = None,
          film_group_stride: int = 0, bias1_off: int = 0, groups: int = 1,
          a_group_col_stride: int = 0, b_group_row_stride: int = 0, out_group_col_stride: int = 0,
-         dil: Optional[Sequence[int]] = None, flags: int = 0) -> torch.Tensor:
+         dil: Optional[Sequence[int]] = None, flags: int = 0,
+         debug_timeline: Optional[torch.Tensor] = None) -> torch.Tensor:
     """out = epilogue(segmented_gemm(a, w)).  `a`: (batches, rows, cols) bf16 (may be a strided view),
     `w`: packed bf16 weight (rows, K).  See include/ns2_b200.h section 1 for the exact semantics."""
     lib = _lib.load()
@@ -107,6 +108,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, n: int, epilogu
     args.film = _ptr(film)
     args.film_group_stride = film_group_stride
     args.flags = int(flags)
+    args.debug_timeline = _ptr(debug_timeline)
     check(lib.ns2_gemm(C.byref(args), _stream(out)), "ns2_gemm")
     return out
 
