@@ -101,6 +101,28 @@ typedef struct ns2_gemm_args {
 int ns2_gemm(const ns2_gemm_args* args, ns2_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * 1b. Weight gradient of a Linear / CausalConv1d tap (autograd's grad_weight = grad_output^T @ input; the reference
+ *     reaches it through loss.backward(), README.md:63, ns2.py:1886):
+ *        dW[g][n, k] += sum_{b, m} dY[b, m, g*dy_group_col_stride + n] * X[b, m - shift_units*dil[g], g*x_group_col_stride + x_col_off + k]
+ *     dY / X: bf16 token-major activations (batches, rows, cols); dW: fp32, ACCUMULATED into (reduce-add), row stride
+ *     dw_row_stride, group g at row g*dw_group_row_stride.  n, k multiples of 32 (n a multiple of 128 when groups > 1).
+ *     Positions outside [0, rows) of a shifted tap contribute zero (the conv's causal padding).  splits = 0: automatic.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct ns2_wgrad_args {
+  const void* dY; int64_t dy_row_stride, dy_batch_stride; int32_t dy_cols;
+  const void* X;  int64_t x_row_stride, x_batch_stride;  int32_t x_cols;
+  int32_t batches, rows;
+  int32_t n, k;
+  int32_t groups, dy_group_col_stride, x_group_col_stride, x_col_off;
+  int32_t dil[NS2_GEMM_MAX_GROUPS];
+  int32_t shift_units;
+  float* dW; int64_t dw_row_stride; int32_t dw_group_row_stride;
+  int32_t splits;
+} ns2_wgrad_args;
+
+int ns2_wgrad(const ns2_wgrad_args* args, ns2_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * 2. Non-causal, unmasked flash attention forward (Attend.forward, attend.py:112-155 with mask=None,
  *    causal=False, dropout=0 — the only configuration the hot path uses).
  *    q/k/v: bf16, head h lives in columns [h*64, h*64+64) of each row; dim_head must be 64.
@@ -116,6 +138,8 @@ typedef struct ns2_attn_args {
   int32_t kernel;   /* NS2_ATTN_AUTO, or force one implementation (tests / tuning) */
   void* debug_timeline; /* bring-up aid, normally NULL: device buffer of 64*16 int64 receiving clock64 stamps of CTA 0
                            of the two-tile kernel (tools/attn_timeline.py) */
+  float* lse;           /* optional (batches, heads, q_len) f32: log2-domain log-sum-exp of the scaled score rows,
+                           saved for ns2_attn_bwd */
 } ns2_attn_args;
 
 #define NS2_ATTN_AUTO 0            /* two-tile kernel when q_len > 128 and kv_len > 64, else one-tile */
@@ -126,6 +150,26 @@ typedef struct ns2_attn_args {
 #define NS2_ATTN_TWO_TILE_LOCKSTEP 5 /* two-tile without the exponential-section turn taking (A/B measurement) */
 
 int ns2_attn_fwd(const ns2_attn_args* args, ns2_stream_t stream);
+
+/* Backward of the above (autograd of F.scaled_dot_product_attention, reached from loss.backward(), ns2.py:1886):
+ *   dq_accum (batches, q_len, heads*64) f32, contiguous, must be ZERO on entry (every key tile adds its share);
+ *   dk / dv: bf16, same layout conventions as k / v;  lse from ns2_attn_fwd;  delta: scratch (batches, heads, q_len) f32. */
+typedef struct ns2_attn_bwd_args {
+  const void* q; int64_t q_row_stride, q_batch_stride;
+  const void* k; int64_t k_row_stride, k_batch_stride;
+  const void* v; int64_t v_row_stride, v_batch_stride;
+  const void* o; int64_t o_row_stride, o_batch_stride;
+  const void* d_o; int64_t do_row_stride, do_batch_stride;
+  const float* lse;
+  float* delta;
+  float* dq_accum;
+  void* dk; int64_t dk_row_stride, dk_batch_stride;
+  void* dv; int64_t dv_row_stride, dv_batch_stride;
+  int32_t batches, heads, q_len, kv_len, dim_head;
+  float scale;
+} ns2_attn_bwd_args;
+
+int ns2_attn_bwd(const ns2_attn_bwd_args* args, ns2_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * 3. RMSNorm (+ learned gamma) (+ FiLM) : RMSNorm.forward ns2.py:736-746.
@@ -240,6 +284,38 @@ int ns2_rvq_decode(const int64_t* codes, int64_t num_frames, int32_t q, int32_t 
 int ns2_rvq_ce(const float* frames, int64_t num_frames, int32_t d, const float* codebooks,
                const float* cb_norm2, int32_t q, int32_t k, const int64_t* own_codes,
                const int64_t* target_codes, float* ce_scratch, float* loss, ns2_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * 8. Backward pass (what autograd runs for the reference's loss.backward(), README.md:63, ns2.py:1886).
+ *    Matrix products: ns2_gemm with transposed weight packs (dgrad; negative shift_units = anti-causal taps) and
+ *    ns2_wgrad.  Between them:
+ *    ns2_rmsnorm_film_bwd : backward of RMSNorm (+learned gamma | +FiLM), ns2.py:736-746.  dxr (fp32 residual-stream
+ *                           gradient) += dx IN PLACE, its bf16 copy is written to dxr_bf16; dfilm[b, :dim] += d(gamma_b),
+ *                           dfilm[b, dim:2dim] += d(beta_b) (atomics); dgamma[:] += d(learned gamma)
+ *    ns2_geglu_bwd        : pre (rows, 2*dp) bf16 in the packed [128 value | 128 gate] tile layout is OVERWRITTEN by its
+ *                           gradient given dg (rows, dp) bf16   (GEGLU, ns2.py:1004-1007)
+ *    ns2_wavenet_gate_bwd : dz of y = tanh(z) sigmoid(z) + res, z = c*gamma_b + beta_b (ns2.py:625-630): dc = dz*gamma_b,
+ *                           dfilm += [sum dz*c | sum dz] per batch / group
+ *    ns2_colsum_bf16      : out[c] += sum_r t[r, c]            (bias gradients)
+ *    ns2_group_sum_bf16   : out[r, c] = sum_g t[r, g*dim + c]  (gradient of an input shared by all dilation columns)
+ *    ns2_mse_bwd          : out = coef[b] * (pred - target), bf16 and/or f32   (seed of the backward pass, ns2.py:1646-1666)
+ *    ns2_film_wgrad       : dw[r, c] += sum_b dfilm[b, r] * t[b, c]  (FiLM projection weights; batch <= 48 per call)
+ *    ns2_attn_bwd         : flash-attention backward (dq, dk, dv) from (q, k, v, o, lse, do)
+ * ------------------------------------------------------------------------------------------------ */
+int ns2_rmsnorm_film_bwd(const float* x, const void* dh_bf16, int64_t rows, int32_t dim, int32_t rows_per_batch,
+                         const float* gamma, const float* film, int64_t film_batch_stride, float* dfilm,
+                         int64_t dfilm_batch_stride, float* dgamma, float* dxr, void* dxr_bf16, ns2_stream_t stream);
+int ns2_geglu_bwd(void* pre_bf16, const void* dg_bf16, int64_t rows, int32_t dp, ns2_stream_t stream);
+int ns2_wavenet_gate_bwd(const void* c_bf16, int64_t c_row_stride, const void* dy_bf16, int64_t dy_row_stride,
+                         void* dc_bf16, int64_t dc_row_stride, int32_t batches, int32_t rows_per_batch, int32_t dim,
+                         int32_t groups, const float* film, int64_t film_batch_stride, int32_t film_group_stride,
+                         float* dfilm, int64_t dfilm_batch_stride, ns2_stream_t stream);
+int ns2_colsum_bf16(const void* t_bf16, int64_t rows, int32_t cols, int64_t row_stride, float* out, ns2_stream_t stream);
+int ns2_group_sum_bf16(const void* t_bf16, int64_t rows, int32_t dim, int32_t groups, void* out_bf16, ns2_stream_t stream);
+int ns2_mse_bwd(const float* pred, const float* target, const float* coef, int32_t batch, int64_t per_sample,
+                void* out_bf16 /* optional */, float* out_f32 /* optional */, ns2_stream_t stream);
+int ns2_film_wgrad(const float* dfilm, const float* t, int32_t batch, int64_t rows, int32_t cols, float* dw,
+                   ns2_stream_t stream);
 
 /* Number of kernel launches issued through this library since load (for bench.py's gpu_launches). */
 int64_t ns2_launch_count(void);

@@ -41,6 +41,17 @@ class GemmArgs(C.Structure):
     ]
 
 
+class WgradArgs(C.Structure):
+    _fields_ = [
+        ("dY", C.c_void_p), ("dy_row_stride", C.c_int64), ("dy_batch_stride", C.c_int64), ("dy_cols", C.c_int32),
+        ("X", C.c_void_p), ("x_row_stride", C.c_int64), ("x_batch_stride", C.c_int64), ("x_cols", C.c_int32),
+        ("batches", C.c_int32), ("rows", C.c_int32), ("n", C.c_int32), ("k", C.c_int32),
+        ("groups", C.c_int32), ("dy_group_col_stride", C.c_int32), ("x_group_col_stride", C.c_int32),
+        ("x_col_off", C.c_int32), ("dil", C.c_int32 * NS2_GEMM_MAX_GROUPS), ("shift_units", C.c_int32),
+        ("dW", C.c_void_p), ("dw_row_stride", C.c_int64), ("dw_group_row_stride", C.c_int32), ("splits", C.c_int32),
+    ]
+
+
 class AttnArgs(C.Structure):
     _fields_ = [
         ("q", C.c_void_p), ("q_row_stride", C.c_int64), ("q_batch_stride", C.c_int64),
@@ -49,7 +60,22 @@ class AttnArgs(C.Structure):
         ("out", C.c_void_p), ("o_row_stride", C.c_int64), ("o_batch_stride", C.c_int64),
         ("batches", C.c_int32), ("heads", C.c_int32), ("q_len", C.c_int32), ("kv_len", C.c_int32),
         ("dim_head", C.c_int32), ("scale", C.c_float), ("kernel", C.c_int32),
-        ("debug_timeline", C.c_void_p),
+        ("debug_timeline", C.c_void_p), ("lse", C.c_void_p),
+    ]
+
+
+class AttnBwdArgs(C.Structure):
+    _fields_ = [
+        ("q", C.c_void_p), ("q_row_stride", C.c_int64), ("q_batch_stride", C.c_int64),
+        ("k", C.c_void_p), ("k_row_stride", C.c_int64), ("k_batch_stride", C.c_int64),
+        ("v", C.c_void_p), ("v_row_stride", C.c_int64), ("v_batch_stride", C.c_int64),
+        ("o", C.c_void_p), ("o_row_stride", C.c_int64), ("o_batch_stride", C.c_int64),
+        ("d_o", C.c_void_p), ("do_row_stride", C.c_int64), ("do_batch_stride", C.c_int64),
+        ("lse", C.c_void_p), ("delta", C.c_void_p), ("dq_accum", C.c_void_p),
+        ("dk", C.c_void_p), ("dk_row_stride", C.c_int64), ("dk_batch_stride", C.c_int64),
+        ("dv", C.c_void_p), ("dv_row_stride", C.c_int64), ("dv_batch_stride", C.c_int64),
+        ("batches", C.c_int32), ("heads", C.c_int32), ("q_len", C.c_int32), ("kv_len", C.c_int32),
+        ("dim_head", C.c_int32), ("scale", C.c_float),
     ]
 
 
@@ -61,7 +87,9 @@ SIGNATURES = {
     "ns2_abi_version": (C.c_int, []),
     "ns2_launch_count": (C.c_int64, []),
     "ns2_gemm": (C.c_int, [C.POINTER(GemmArgs), _P]),
+    "ns2_wgrad": (C.c_int, [C.POINTER(WgradArgs), _P]),
     "ns2_attn_fwd": (C.c_int, [C.POINTER(AttnArgs), _P]),
+    "ns2_attn_bwd": (C.c_int, [C.POINTER(AttnBwdArgs), _P]),
     "ns2_rmsnorm_film": (C.c_int, [_P, _I64, _I64, _I32, _I32, _P, _P, _I64, _P, _I64, _P]),
     "ns2_rmsnorm_f32": (C.c_int, [_P, _I64, _I64, _I32, _P, _P, _I64, _P]),
     "ns2_time_cond": (C.c_int, [_P, _I32, _P, _I32, _P, _P, _I32, _P, _I64, _P]),
@@ -76,6 +104,13 @@ SIGNATURES = {
     "ns2_ddim_step": (C.c_int, [_P, _P, _P, _P, _P, _P, _I32, _I64, _I32, _P]),
     "ns2_cfg_combine": (C.c_int, [_P, _P, _F, _I64, _P, _P]),
     "ns2_x_start": (C.c_int, [_P, _P, _P, _P, _I32, _I64, _P, _I32, _P]),
+    "ns2_rmsnorm_film_bwd": (C.c_int, [_P, _P, _I64, _I32, _I32, _P, _P, _I64, _P, _I64, _P, _P, _P, _P]),
+    "ns2_geglu_bwd": (C.c_int, [_P, _P, _I64, _I32, _P]),
+    "ns2_wavenet_gate_bwd": (C.c_int, [_P, _I64, _P, _I64, _P, _I64, _I32, _I32, _I32, _I32, _P, _I64, _I32, _P, _I64, _P]),
+    "ns2_colsum_bf16": (C.c_int, [_P, _I64, _I32, _I64, _P, _P]),
+    "ns2_group_sum_bf16": (C.c_int, [_P, _I64, _I32, _I32, _P, _P]),
+    "ns2_mse_bwd": (C.c_int, [_P, _P, _P, _I32, _I64, _P, _P, _P]),
+    "ns2_film_wgrad": (C.c_int, [_P, _P, _I32, _I64, _I32, _P, _P]),
     "ns2_rvq_prepare": (C.c_int, [_P, _I32, _I32, _I32, _P, _P, _P, _P]),
     "ns2_rvq_encode": (C.c_int, [_P, _I64, _I32, _P, _P, _P, _P, _I32, _I32, _P, _P, _P]),
     "ns2_rvq_decode": (C.c_int, [_P, _I64, _I32, _I32, _I32, _P, _P, _P]),

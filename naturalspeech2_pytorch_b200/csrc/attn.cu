@@ -46,6 +46,7 @@ struct AttnDev {
   long long o_rs, o_bs;
   int q_len, kv_len;
   float scale_log2e;
+  float* lse;   // optional (batches, heads, q_len): log2-domain log-sum-exp of the scaled scores, for the backward pass
 };
 
 // bf16 pair from two non-negative finite floats with round-half-up done on the integer pipe (IADD + PRMT): the
@@ -281,6 +282,8 @@ __global__ void __launch_bounds__(192, 2) attn_fwd_kernel(const __grid_constant_
 
     if (q0 + row < p.q_len) {
       const float inv = 1.0f / l_run;
+      if (p.lse != nullptr)
+        p.lse[(static_cast<long long>(b) * gridDim.y + head) * p.q_len + q0 + row] = m_run + log2f(l_run);
       __nv_bfloat16* op = p.out + static_cast<long long>(b) * p.o_bs +
                           static_cast<long long>(q0 + row) * p.o_rs + head * DH;
       uint4* o4 = reinterpret_cast<uint4*>(op);
@@ -344,6 +347,7 @@ struct Attn2Dev {
   int q_len, kv_len, heads;
   int q_pairs, num_items;
   float scale_log2e;
+  float* lse;            // optional (batches, heads, q_len), see AttnDev
   long long* timeline;   // bring-up aid (ns2_attn_args.debug_timeline): clock64 stamps of CTA 0, else NULL
 };
 
@@ -727,6 +731,8 @@ __global__ void __launch_bounds__(attn2::THREADS, 1) attn2_fwd_kernel(const __gr
       const int qrow = q0 + w * BQ + row;
       if (qrow < p.q_len) {
         const float inv = 1.0f / l_run;
+        if (p.lse != nullptr)
+          p.lse[(static_cast<long long>(b) * p.heads + head) * p.q_len + qrow] = m_run + log2f(l_run);
         __nv_bfloat16* op = p.out + static_cast<long long>(b) * p.o_bs + static_cast<long long>(qrow) * p.o_rs +
                             head * DH;
         uint4* o4 = reinterpret_cast<uint4*>(op);
@@ -796,6 +802,7 @@ extern "C" int ns2_attn_fwd(const ns2_attn_args* a, ns2_stream_t stream_) {
   dev.q_len = a->q_len;
   dev.kv_len = a->kv_len;
   dev.scale_log2e = a->scale * 1.4426950408889634f;
+  dev.lse = a->lse;
 
   // kernel choice: the two-tile kernel (256 queries x 128-key tiles per CTA, P and O in TMEM) for self-attention sized
   // problems; the single-tile kernel (128 queries x 64-key tiles) for short key sequences (cross attention over the 32
@@ -838,6 +845,7 @@ extern "C" int ns2_attn_fwd(const ns2_attn_args* a, ns2_stream_t stream_) {
   d2.num_items = d2.q_pairs * a->heads * a->batches;
   d2.scale_log2e = a->scale * 1.4426950408889634f;
   d2.timeline = reinterpret_cast<long long*>(a->debug_timeline);
+  d2.lse = a->lse;
   const int grid2 = d2.num_items < num_sms() ? d2.num_items : num_sms();
   auto launch2 = [&](auto kern) -> int {
     NS2_CUDA_CHECK(set_max_smem_once(kern, attn2::SMEM_BYTES));

@@ -877,8 +877,8 @@ extern "C" int ns2_gemm(const ns2_gemm_args* a, ns2_stream_t stream_) {
               "ns2_gemm: strides must be multiples of 8 elements (16 bytes)");
   for (int s = 0; s < a->num_segs; ++s) {
     const ns2_gemm_seg& sg = a->segs[s];
-    NS2_REQUIRE(sg.k_len > 0 && sg.acc >= 0 && sg.acc <= 1 && sg.shift_units >= 0,
-                "ns2_gemm: bad segment %d", s);
+    // negative shift_units = rows AFTER the output position (anti-causal taps: the dgrad of a causal conv)
+    NS2_REQUIRE(sg.k_len > 0 && sg.acc >= 0 && sg.acc <= 1, "ns2_gemm: bad segment %d", s);
     const bool ends_at_edge = (sg.b_col_off + sg.k_len == a->b_cols) &&
                               (sg.a_col_off + sg.k_len == a->a_cols) && a->groups == 1;
     NS2_REQUIRE(sg.k_len % BK == 0 || ends_at_edge,

@@ -235,9 +235,8 @@ class NaturalSpeech2(nn.Module):
         return audio
 
     # ------------------------------------------------------------------------------------------
-    # training loss (forward only)
+    # training loss (differentiable: `loss.backward()` runs the hand-written backward kernels)
     # ------------------------------------------------------------------------------------------
-    @torch.no_grad()
     def forward(self, audio, text=None, text_lens=None, mel=None, mel_lens=None, codes=None, prompt=None,
                 pitch=None, *args, prompt_enc=None, cond=None, times=None, noise=None, **kwargs):
         """ns2.py:1503-1684 -> scalar diffusion loss (the only term the reference returns).
@@ -273,7 +272,11 @@ class NaturalSpeech2(nn.Module):
         target = torch.empty_like(audio)
         ops.q_sample(audio, noise, alpha, sigma, noised, target, objective=self.objective)  # ns2.py:1631-1644
         pred = self.model(noised, times, prompt=prompt_enc, cond=cond)  # ns2.py:1635
-        loss = ops.mse_rows(pred, target, torch.empty(batch, device=device))  # ns2.py:1646-1647
+        if pred.requires_grad:
+            from .training import MseRowsFunction
+            loss = MseRowsFunction.apply(pred, target)                  # ns2.py:1646-1647, with a backward kernel
+        else:
+            loss = ops.mse_rows(pred, target, torch.empty(batch, device=device))
         # min-SNR weight on (B,)-sized tensors, with the reference's exact broadcasting (ns2.py:1651-1666):
         # loss is (B,), loss_weight is (B,1,1) -> the product is (B,1,B) before .mean()
         a3, s3 = alpha.view(-1, 1, 1), sigma.view(-1, 1, 1)
@@ -292,7 +295,7 @@ class NaturalSpeech2(nn.Module):
             return loss
         # cross entropy of the predicted x_start against the codec's codes (ns2.py:1673-1684)
         x_start = torch.empty_like(audio)
-        ops.x_start_from_pred(audio, pred, alpha, sigma, x_start, objective=self.objective)
+        ops.x_start_from_pred(audio, pred.detach(), alpha, sigma, x_start, objective=self.objective)
         _, ce_loss = self.codec.rq(x_start, codes)
         return loss + self.rvq_cross_entropy_loss_weight * ce_loss
 

@@ -476,17 +476,38 @@ class Model(nn.Module):
         null_logits = self.forward(*args, cond_drop_prob=1., **kwargs)
         return ops.cfg_combine(logits, null_logits, cond_scale, logits)   # in place into the (fresh) first output
 
-    @torch.no_grad()
+    def packed_transposed(self) -> Dict[str, torch.Tensor]:
+        """Transposed bf16 packs for the dgrad GEMMs of the backward pass (training.py), cached with `packed()`."""
+        P = self.packed()
+        if getattr(self, "_packed_T_of", None) is not P:
+            from .training import pack_transposed
+            with torch.no_grad():
+                self._packed_T = pack_transposed(self)
+            self._packed_T_of = P
+        return self._packed_T
+
     def forward(self, x, times, prompt=None, prompt_mask=None, cond=None, cond_drop_prob=None, *,
                 out: Optional[torch.Tensor] = None, _conditioning: Optional[dict] = None):
         """x (B, N, dim) fp32, times (B,) in [0, 1] -> (B, N, dim) fp32   (ns2.py:929-1000).
 
         Returns a fresh tensor, like the reference; pass `out=` (contiguous fp32 (B, N, dim)) to have the prediction
-        written into a buffer the caller owns instead.  Inference only (no autograd graph is recorded).
+        written into a buffer the caller owns instead.  In train mode (`model.train()`, the nn.Module default) with
+        gradients enabled the call records one autograd node whose backward runs the hand-written backward kernels
+        (`training.py`); after `model.eval()` or under `torch.no_grad()` it is the inference path and nothing is saved.
 
         With `use_cuda_graphs` the whole step (every kernel launch below) is captured once per
         (B, N, drop-prob, conditioning shapes) and replayed; eligible when no RNG draw and no per-call host work is
         involved, i.e. unconditional models or cached conditioning with cond_drop_prob in {0, 1}."""
+        if self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            # training: one autograd node whose backward runs the hand-written kernels (training.py)
+            from .training import DenoiserFunction
+            if self.condition_on_prompt or prompt_mask is not None or out is not None:
+                raise NotImplementedError("the backward pass covers the unconditional denoiser (no out=, no prompt)")
+            return DenoiserFunction.apply(self, x, times, *self.parameters())
+        with torch.no_grad():
+            return self._forward_nograd(x, times, prompt, prompt_mask, cond, cond_drop_prob, out, _conditioning)
+
+    def _forward_nograd(self, x, times, prompt, prompt_mask, cond, cond_drop_prob, out, _conditioning):
         if out is not None:
             if not (out.is_cuda and out.dtype == torch.float32 and out.is_contiguous()
                     and tuple(out.shape) == tuple(x.shape)):

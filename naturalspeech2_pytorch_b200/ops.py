@@ -113,6 +113,35 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, n: int, epilogu
     return out
 
 
+def wgrad(dy: torch.Tensor, x: torch.Tensor, dw: torch.Tensor, *, n: int, k: int, shift_units: int = 0,
+          x_col_off: int = 0, groups: int = 1, dy_group_col_stride: int = 0, x_group_col_stride: int = 0,
+          dw_group_row_stride: int = 0, dil: Optional[Sequence[int]] = None, splits: int = 0) -> torch.Tensor:
+    """dw[g][:n, :k] += dy[..., g-th n columns]^T @ x[..., rows shifted by shift_units*dil[g], g-th k columns].
+    dy, x: (batches, rows, cols) bf16 (strided views are fine); dw: fp32 2-D (rows >= groups' n rows, cols >= k)."""
+    lib = _lib.load()
+    _req(dy, torch.bfloat16, "dy")
+    _req(x, torch.bfloat16, "x")
+    _req(dw, torch.float32, "dw")
+    if dy.dim() != 3 or x.dim() != 3 or dy.shape[:2] != x.shape[:2] or dw.dim() != 2:
+        raise ValueError("wgrad: dy and x must be (batches, rows, cols) with equal leading dims; dw 2-D")
+    if groups > 1 and n % 128 != 0:
+        raise ValueError("wgrad: n must be a multiple of 128 for grouped weights")
+    args = _lib.WgradArgs()
+    args.dY, args.dy_row_stride, args.dy_batch_stride, args.dy_cols = dy.data_ptr(), dy.stride(1), dy.stride(0), dy.shape[2]
+    args.X, args.x_row_stride, args.x_batch_stride, args.x_cols = x.data_ptr(), x.stride(1), x.stride(0), x.shape[2]
+    args.batches, args.rows = dy.shape[0], dy.shape[1]
+    args.n, args.k = n, k
+    args.groups = groups
+    args.dy_group_col_stride, args.x_group_col_stride, args.x_col_off = dy_group_col_stride, x_group_col_stride, x_col_off
+    for g in range(_lib.NS2_GEMM_MAX_GROUPS):
+        args.dil[g] = int(dil[g]) if dil is not None and g < len(dil) else 1
+    args.shift_units = shift_units
+    args.dW, args.dw_row_stride, args.dw_group_row_stride = dw.data_ptr(), dw.stride(0), dw_group_row_stride
+    args.splits = splits
+    check(lib.ns2_wgrad(C.byref(args), _stream(dw)), "ns2_wgrad")
+    return dw
+
+
 def conv3_segs(k_len: int, tap_stride: Optional[int] = None, acc: int = 0, a_col_off: int = 0,
                b_col_off: int = 0) -> list:
     """Segments of a causal k=3 conv whose packed weight holds tap t at columns [t*tap_stride, +k_len):
@@ -129,7 +158,7 @@ ATTN_AUTO, ATTN_ONE_TILE, ATTN_TWO_TILE, ATTN_TWO_TILE_POLY2, ATTN_TWO_TILE_POLY
 
 def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tensor, *, heads: int,
               scale: Optional[float] = None, kernel: int = ATTN_AUTO,
-              debug_timeline: Optional[torch.Tensor] = None) -> torch.Tensor:
+              debug_timeline: Optional[torch.Tensor] = None, lse: Optional[torch.Tensor] = None) -> torch.Tensor:
     """q: (B, Nq, heads*64), k/v: (B, Nk, heads*64) bf16 (strided views into a fused projection are fine)."""
     lib = _lib.load()
     for name, t in (("q", q), ("k", k), ("v", v), ("out", out)):
@@ -146,6 +175,11 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tens
     args.scale = float(scale if scale is not None else 64 ** -0.5)
     args.kernel = int(kernel)
     args.debug_timeline = _ptr(debug_timeline)
+    if lse is not None:
+        _req(lse, torch.float32, "lse")
+        if not lse.is_contiguous() or tuple(lse.shape) != (q.shape[0], heads, q.shape[1]):
+            raise ValueError("lse must be a contiguous (B, heads, Nq) float tensor")
+    args.lse = _ptr(lse)
     check(lib.ns2_attn_fwd(C.byref(args), _stream(out)), "ns2_attn_fwd")
     return out
 
@@ -438,3 +472,142 @@ def rvq_ce(frames: torch.Tensor, codebooks: torch.Tensor, cn2: torch.Tensor, own
     check(lib.ns2_rvq_ce(fr.data_ptr(), F, D, cb.data_ptr(), cn2.data_ptr(), Q, K, own_codes.data_ptr(),
                          target_codes.data_ptr(), scratch.data_ptr(), loss.data_ptr(), _stream(fr)), "ns2_rvq_ce")
     return loss
+
+
+# --------------------------------------------------------------------------------------------------
+# backward pass
+# --------------------------------------------------------------------------------------------------
+def attention_bwd(q, k, v, o, d_o, lse, dq_accum, dk, dv, *, heads: int, scale: Optional[float] = None,
+                  delta: Optional[torch.Tensor] = None):
+    """(dq_accum f32 (B, Nq, inner) += dQ, dk, dv bf16) of softmax(q k^T scale) v given d_o; dq_accum must be zeroed."""
+    lib = _lib.load()
+    for name, t in (("q", q), ("k", k), ("v", v), ("o", o), ("d_o", d_o), ("dk", dk), ("dv", dv)):
+        _req(t, torch.bfloat16, name)
+        if t.dim() != 3 or t.shape[2] != heads * 64:
+            raise ValueError(f"{name} must be (B, N, heads*64), got {tuple(t.shape)}")
+    _req(lse, torch.float32, "lse")
+    _req(dq_accum, torch.float32, "dq_accum")
+    B, Nq, Nk = q.shape[0], q.shape[1], k.shape[1]
+    if not dq_accum.is_contiguous() or tuple(dq_accum.shape) != (B, Nq, heads * 64):
+        raise ValueError("dq_accum must be contiguous (B, Nq, heads*64) float32")
+    if delta is None:
+        delta = torch.empty(B, heads, Nq, device=q.device, dtype=torch.float32)
+    a = _lib.AttnBwdArgs()
+    a.q, a.q_row_stride, a.q_batch_stride = q.data_ptr(), q.stride(1), q.stride(0)
+    a.k, a.k_row_stride, a.k_batch_stride = k.data_ptr(), k.stride(1), k.stride(0)
+    a.v, a.v_row_stride, a.v_batch_stride = v.data_ptr(), v.stride(1), v.stride(0)
+    a.o, a.o_row_stride, a.o_batch_stride = o.data_ptr(), o.stride(1), o.stride(0)
+    a.d_o, a.do_row_stride, a.do_batch_stride = d_o.data_ptr(), d_o.stride(1), d_o.stride(0)
+    a.lse, a.delta, a.dq_accum = lse.data_ptr(), delta.data_ptr(), dq_accum.data_ptr()
+    a.dk, a.dk_row_stride, a.dk_batch_stride = dk.data_ptr(), dk.stride(1), dk.stride(0)
+    a.dv, a.dv_row_stride, a.dv_batch_stride = dv.data_ptr(), dv.stride(1), dv.stride(0)
+    a.batches, a.heads, a.q_len, a.kv_len, a.dim_head = B, heads, Nq, Nk, 64
+    a.scale = float(scale if scale is not None else 64 ** -0.5)
+    check(lib.ns2_attn_bwd(C.byref(a), _stream(dq_accum)), "ns2_attn_bwd")
+    return dq_accum, dk, dv
+
+
+def rmsnorm_film_bwd(x, dh, dxr, dxr_bf, *, rows_per_batch: int, gamma=None, film=None, dfilm=None, dgamma=None):
+    """dxr (f32, in place) += d/dx of rmsnorm_film(x) given dh (bf16); dxr_bf = bf16(dxr); dfilm / dgamma accumulate."""
+    lib = _lib.load()
+    _req(x, torch.float32, "x")
+    _req(dh, torch.bfloat16, "dh")
+    _req(dxr, torch.float32, "dxr")
+    _req(dxr_bf, torch.bfloat16, "dxr_bf")
+    for t in (x, dh, dxr, dxr_bf):
+        if not t.is_contiguous():
+            raise ValueError("rmsnorm_film_bwd needs contiguous tensors")
+    D = x.shape[-1]
+    rows = x.numel() // D
+    film_bs = dfilm_bs = 0
+    if film is not None:
+        _req(film, torch.float32, "film")
+        _req(dfilm, torch.float32, "dfilm")
+        film_bs, dfilm_bs = film.stride(0), dfilm.stride(0)
+    check(lib.ns2_rmsnorm_film_bwd(x.data_ptr(), dh.data_ptr(), rows, D, rows_per_batch, _ptr(gamma), _ptr(film), film_bs,
+                                   _ptr(dfilm), dfilm_bs, _ptr(dgamma), dxr.data_ptr(), dxr_bf.data_ptr(), _stream(dxr)),
+          "ns2_rmsnorm_film_bwd")
+    return dxr
+
+
+def geglu_bwd(pre, dg):
+    """pre (rows, 2*Dp) bf16 packed [128 value | 128 gate] tiles -> overwritten by its gradient given dg (rows, Dp)."""
+    lib = _lib.load()
+    _req(pre, torch.bfloat16, "pre")
+    _req(dg, torch.bfloat16, "dg")
+    if not (pre.is_contiguous() and dg.is_contiguous()) or pre.shape[-1] != 2 * dg.shape[-1]:
+        raise ValueError("geglu_bwd: pre (.., 2*Dp) and dg (.., Dp) must be contiguous")
+    dp = dg.shape[-1]
+    check(lib.ns2_geglu_bwd(pre.data_ptr(), dg.data_ptr(), dg.numel() // dp, dp, _stream(pre)), "ns2_geglu_bwd")
+    return pre
+
+
+def wavenet_gate_bwd(c, dy, dc, film, dfilm, *, dim: int, groups: int, film_group_stride: int):
+    """c, dy, dc: (B, N, >= groups*dim) bf16 views (first groups*dim columns used); film/dfilm (B, ...) f32 views whose
+    row b holds, for group g at g*film_group_stride, [gamma | beta]."""
+    lib = _lib.load()
+    for name, t in (("c", c), ("dy", dy), ("dc", dc)):
+        _req(t, torch.bfloat16, name)
+        if t.dim() != 3 or t.stride(0) != t.shape[1] * t.stride(1):
+            raise ValueError(f"{name} must be (B, N, cols) with uniformly strided rows")
+    _req(film, torch.float32, "film")
+    _req(dfilm, torch.float32, "dfilm")
+    B, N = c.shape[0], c.shape[1]
+    check(lib.ns2_wavenet_gate_bwd(c.data_ptr(), c.stride(1), dy.data_ptr(), dy.stride(1), dc.data_ptr(), dc.stride(1), B,
+                                   N, dim, groups, film.data_ptr(), film.stride(0), film_group_stride, dfilm.data_ptr(),
+                                   dfilm.stride(0), _stream(dc)), "ns2_wavenet_gate_bwd")
+    return dc
+
+
+def colsum(t, out):
+    """out[c] (f32) += sum over all leading dims of t[..., c] (bf16; last dim contiguous, uniform row stride)."""
+    lib = _lib.load()
+    _req(t, torch.bfloat16, "t")
+    _req(out, torch.float32, "out")
+    cols = t.shape[-1]
+    rows = t.numel() // cols
+    rs = t.stride(-2) if t.dim() >= 2 else cols
+    if t.dim() == 3 and t.stride(0) != t.shape[1] * t.stride(1):
+        raise ValueError("colsum: rows must be uniformly strided")
+    check(lib.ns2_colsum_bf16(t.data_ptr(), rows, cols, rs, out.data_ptr(), _stream(out)), "ns2_colsum_bf16")
+    return out
+
+
+def group_sum(t, out, *, dim: int, groups: int):
+    lib = _lib.load()
+    _req(t, torch.bfloat16, "t")
+    _req(out, torch.bfloat16, "out")
+    if not (t.is_contiguous() and out.is_contiguous()):
+        raise ValueError("group_sum needs contiguous tensors")
+    check(lib.ns2_group_sum_bf16(t.data_ptr(), out.numel() // dim, dim, groups, out.data_ptr(), _stream(out)),
+          "ns2_group_sum_bf16")
+    return out
+
+
+def mse_bwd(pred, target, coef, out_bf=None, out_f32=None):
+    """coef[b] * (pred - target) as bf16 and/or f32: the seed of the backward pass."""
+    lib = _lib.load()
+    for name, t in (("pred", pred), ("target", target), ("coef", coef)):
+        _req(t, torch.float32, name)
+    if out_bf is not None:
+        _req(out_bf, torch.bfloat16, "out_bf")
+    if out_f32 is not None:
+        _req(out_f32, torch.float32, "out_f32")
+    B = pred.shape[0]
+    check(lib.ns2_mse_bwd(pred.data_ptr(), target.data_ptr(), coef.data_ptr(), B, pred.numel() // B, _ptr(out_bf),
+                          _ptr(out_f32), _stream(pred)), "ns2_mse_bwd")
+    return out_bf if out_bf is not None else out_f32
+
+
+def film_wgrad(dfilm, t, dw):
+    """dw (rows, cols) f32 += dfilm (B, rows)^T @ t (B, cols)."""
+    lib = _lib.load()
+    for name, x in (("dfilm", dfilm), ("t", t), ("dw", dw)):
+        _req(x, torch.float32, name)
+        if not x.is_contiguous():
+            raise ValueError(f"{name} must be contiguous")
+    B, rows = dfilm.shape
+    for b0 in range(0, B, 32):
+        check(lib.ns2_film_wgrad(dfilm[b0:b0 + 32].data_ptr(), t[b0:b0 + 32].data_ptr(), min(32, B - b0), rows, t.shape[1],
+                                 dw.data_ptr(), _stream(dw)), "ns2_film_wgrad")
+    return dw

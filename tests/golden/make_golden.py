@@ -174,6 +174,47 @@ def diffusion_goldens(ns2):
                         ddim_out=sample.numpy(), timesteps=np.array(4), **extra)
 
 
+def gradient_goldens(ns2):
+    """d(loss)/d(theta) of the reference in fp64 (uncond_small weights, the diffusion golden's latents/times/noise):
+    every parameter gradient's norm plus a few whole tensors — what the `-m gpu` backward test compares with."""
+    kwargs, B, N, _, _ = CASES["uncond_small"]
+    z = np.load(HERE / "diffusion_uncond_small.npz")
+    model = ns2.Model(**kwargs)
+    fill_module(model, seed=1234)
+    model = model.double()
+    diff = ns2.NaturalSpeech2(model=model, target_sample_hz=24000, timesteps=4)
+    latents = torch.from_numpy(z["latents"]).double()
+    times = torch.from_numpy(z["times"]).double()
+    noise = torch.from_numpy(z["noise"]).double()
+    # ns2.py:1621-1666 with the recorded draws
+    gamma = diff.gamma_schedule(times)
+    alpha, sigma = ns2.gamma_to_alpha_sigma(gamma[:, None, None], diff.scale)
+    noised = alpha * latents + sigma * noise
+    pred = model(noised, times)
+    target = alpha * noise - sigma * latents
+    loss = ((pred - target) ** 2).reshape(B, -1).mean(dim=1)
+    snr = (alpha * alpha) / (sigma * sigma)
+    weight = snr.clamp(max=diff.min_snr_gamma) / (snr + 1)
+    loss = (loss * weight).mean()
+    loss.backward()
+    out = {"loss": np.array(loss.item())}
+    keep = ("transformer.to_pred.1.weight", "transformer.layers.0.1.to_q.weight", "transformer.layers.1.5.2.1.weight",
+            "transformer.layers.0.5.0.bias", "transformer.layers.1.4.to_gamma_beta.weight", "wavenet.init_conv.weight",
+            "wavenet.stacks.0.blocks.2.conv.weight", "wavenet.stacks.1.blocks.0.skip_conv.weight",
+            "wavenet.stacks.1.blocks.1.to_time_cond.bias", "to_time_cond.1.weight", "to_time_cond.0.weights",
+            "transformer.to_pred.0.gamma", "wavenet.final_conv.bias")
+    names, norms = [], []
+    for n, p in model.named_parameters():
+        names.append(n)
+        norms.append(p.grad.norm().item())
+        if n in keep:
+            out["grad::" + n] = p.grad.numpy().astype(np.float32)
+    out["names"] = np.array(names)
+    out["norms"] = np.array(norms)
+    print(f"gradients: loss={loss.item():.6f} params={len(names)} total grad norm={np.sqrt((np.array(norms) ** 2).sum()):.4f}")
+    np.savez_compressed(HERE / "grads_uncond_small.npz", **out)
+
+
 def rvq_goldens():
     """Codes from the HF transformers port of Encodec's residual VQ (fp32 formula) on seeded codebooks.
     Inputs are regenerated from seeds by param_fill.rvq_fixture_inputs(); only the outputs are stored."""
@@ -221,6 +262,8 @@ def main():
             run_case(ns2, name, kwargs, B, N, Np, L, big=True)
     if not only or "diffusion" in only:
         diffusion_goldens(ns2)
+    if not only or "grads" in only:
+        gradient_goldens(ns2)
 
 
 if __name__ == "__main__":
