@@ -316,6 +316,8 @@ int ns2_mse_bwd(const float* pred, const float* target, const float* coef, int32
                 void* out_bf16 /* optional */, float* out_f32 /* optional */, ns2_stream_t stream);
 int ns2_film_wgrad(const float* dfilm, const float* t, int32_t batch, int64_t rows, int32_t cols, float* dw,
                    ns2_stream_t stream);
+/*    ns2_accum_bf16       : acc (f32) += t (bf16); acc_bf16 (optional) = bf16(acc)   (joins a branch gradient) */
+int ns2_accum_bf16(float* acc, const void* t_bf16, int64_t count, void* acc_bf16, ns2_stream_t stream);
 
 /* Number of kernel launches issued through this library since load (for bench.py's gpu_launches). */
 int64_t ns2_launch_count(void);

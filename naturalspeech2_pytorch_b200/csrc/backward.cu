@@ -302,6 +302,20 @@ __global__ void __launch_bounds__(256) cast_pair_kernel(const float4* __restrict
   }
 }
 
+// acc (fp32) += t (bf16); acc_bf = bf16(acc): joins a branch gradient into a residual-stream gradient
+__global__ void __launch_bounds__(256) accum_bf16_kernel(float4* __restrict__ acc, const uint2* __restrict__ t, long long n4,
+                                                         uint2* __restrict__ acc_bf) {
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float4 a = acc[i];
+    const uint2 w = __ldg(t + i);
+    const float2 lo = bf2_to_f2(w.x), hi = bf2_to_f2(w.y);
+    a.x += lo.x; a.y += lo.y; a.z += hi.x; a.w += hi.y;
+    acc[i] = a;
+    if (acc_bf != nullptr) acc_bf[i] = make_uint2(f2_to_bf2(a.x, a.y), f2_to_bf2(a.z, a.w));
+  }
+}
+
 // dW[r, c] += sum_b dfilm[b, r] * t[b, c]   (FiLM projection weights, contraction over the batch only)
 __global__ void __launch_bounds__(256) film_wgrad_kernel(const float* __restrict__ dfilm, const float* __restrict__ t,
                                                          int batch, long long rows, int cols, float* __restrict__ dw) {
@@ -424,6 +438,15 @@ extern "C" int ns2_mse_bwd(const float* pred, const float* target, const float* 
                                                                       reinterpret_cast<const float4*>(target), coef,
                                                                       per_sample / 4, reinterpret_cast<uint2*>(out_bf16),
                                                                       reinterpret_cast<float4*>(out_f32));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  NS2_CUDA_CHECK(cudaGetLastError());
+  return kOk;
+}
+
+extern "C" int ns2_accum_bf16(float* acc, const void* t_bf16, int64_t count, void* acc_bf16, ns2_stream_t stream_) {
+  NS2_REQUIRE(acc && t_bf16 && count > 0 && count % 4 == 0, "accum_bf16: bad arguments");
+  accum_bf16_kernel<<<grid_1d(count / 4), 256, 0, static_cast<cudaStream_t>(stream_)>>>(
+      reinterpret_cast<float4*>(acc), reinterpret_cast<const uint2*>(t_bf16), count / 4, reinterpret_cast<uint2*>(acc_bf16));
   g_launches.fetch_add(1, std::memory_order_relaxed);
   NS2_CUDA_CHECK(cudaGetLastError());
   return kOk;

@@ -501,9 +501,9 @@ class Model(nn.Module):
         if self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
             # training: one autograd node whose backward runs the hand-written kernels (training.py)
             from .training import DenoiserFunction
-            if self.condition_on_prompt or prompt_mask is not None or out is not None:
-                raise NotImplementedError("the backward pass covers the unconditional denoiser (no out=, no prompt)")
-            return DenoiserFunction.apply(self, x, times, *self.parameters())
+            if prompt_mask is not None or out is not None or _conditioning is not None:
+                raise NotImplementedError("training mode takes (x, times[, prompt, cond]): no out=, prompt_mask or cached conditioning")
+            return DenoiserFunction.apply(self, x, times, prompt, cond, cond_drop_prob, *self.parameters())
         with torch.no_grad():
             return self._forward_nograd(x, times, prompt, prompt_mask, cond, cond_drop_prob, out, _conditioning)
 

@@ -611,3 +611,16 @@ def film_wgrad(dfilm, t, dw):
         check(lib.ns2_film_wgrad(dfilm[b0:b0 + 32].data_ptr(), t[b0:b0 + 32].data_ptr(), min(32, B - b0), rows, t.shape[1],
                                  dw.data_ptr(), _stream(dw)), "ns2_film_wgrad")
     return dw
+
+
+def accum_bf16(acc, t, acc_bf=None):
+    """acc (f32, contiguous) += t (bf16, contiguous, same numel); acc_bf (optional) = bf16(acc)."""
+    lib = _lib.load()
+    _req(acc, torch.float32, "acc")
+    _req(t, torch.bfloat16, "t")
+    if not (acc.is_contiguous() and t.is_contiguous()) or acc.numel() != t.numel():
+        raise ValueError("accum_bf16 needs contiguous tensors of equal size")
+    if acc_bf is not None:
+        _req(acc_bf, torch.bfloat16, "acc_bf")
+    check(lib.ns2_accum_bf16(acc.data_ptr(), t.data_ptr(), acc.numel(), _ptr(acc_bf), _stream(acc)), "ns2_accum_bf16")
+    return acc

@@ -1,8 +1,9 @@
-"""Data-parallel plumbing: one process per GPU, independent samples per rank, one scalar collective.
+"""Data-parallel plumbing: one process per GPU, independent samples per rank.
 
-`Model.forward` has no cross-sample op (norms are per token, attention per sample), so the path shards over the
-batch with NO data-path collective; the only exchange is the all-reduce of the scalar loss.
-The reference delegates this to HF accelerate / torch DDP (ns2.py:1723-1726, 1886).
+`Model.forward` has no cross-sample op (norms are per token, attention per sample), so the forward path shards over
+the batch with NO data-path collective; the exchanges are the all-reduce of the scalar loss and, when
+training, of the parameter gradients (`GradReducer`).  The reference delegates both to HF accelerate /
+torch DDP (ns2.py:1723-1726, 1886).
 """
 from __future__ import annotations
 
@@ -52,3 +53,68 @@ def global_mean_loss(local_loss: torch.Tensor, local_count: int) -> torch.Tensor
                        torch.tensor(float(local_count), device=local_loss.device)))
     dist.all_reduce(buf, op=dist.ReduceOp.SUM)
     return buf[0] / buf[1]
+
+
+class GradReducer:
+    """Gradient all-reduce overlapped with the backward pass (what DDP's bucketed reducer does for the reference,
+    ns2.py:1723-1726, 1886).
+
+    `Model.grad_reducer = GradReducer()` makes the denoiser's backward hand every packed gradient buffer to `reduce()`
+    the moment it is final (one transformer layer / wavenet stack at a time, in reverse order): the NCCL all-reduce
+    (average over ranks) is issued asynchronously on the communication stream and runs over NVLink/NVSwitch while the
+    remaining layers' dgrad / wgrad kernels execute; `finish()` (called before the gradients are returned to autograd)
+    makes the compute stream wait for the outstanding collectives.  Buffers smaller than `coalesce_below` bytes are
+    gathered and sent as one flat message at the end instead of one latency-bound collective each."""
+
+    def __init__(self, group=None, coalesce_below: int = 1 << 20):
+        self.group = group
+        self.coalesce_below = coalesce_below
+        self._pending = []
+        self._small = []
+        self._seen = set()
+        self.bytes_reduced = 0
+
+    @property
+    def active(self) -> bool:
+        return dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1
+
+    def reduce(self, t: torch.Tensor) -> None:
+        base = t._base if t._base is not None else t
+        key = (base.data_ptr(), base.numel())   # several gradients are views of one packed buffer: reduce it once
+        if not self.active or key in self._seen or base.numel() == 0:
+            return
+        self._seen.add(key)
+        if not base.is_contiguous():
+            raise ValueError("GradReducer needs the packed gradient buffers to be contiguous")
+        if base.numel() * base.element_size() < self.coalesce_below:
+            self._small.append(base)
+            return
+        self.bytes_reduced += base.numel() * base.element_size()
+        self._pending.append(dist.all_reduce(base, op=dist.ReduceOp.AVG if base.is_cuda else dist.ReduceOp.SUM,
+                                             group=self.group, async_op=True))
+        if not base.is_cuda:   # gloo has no AVG: scale after the wait (CPU tests)
+            self._pending[-1] = (self._pending[-1], base)
+
+    def reduce_all(self, grads: dict) -> None:
+        for g in grads.values():
+            self.reduce(g)
+
+    def finish(self) -> None:
+        if self._small:
+            flat = torch.cat([b.reshape(-1) for b in self._small])
+            cuda = flat.is_cuda
+            dist.all_reduce(flat, op=dist.ReduceOp.AVG if cuda else dist.ReduceOp.SUM, group=self.group)
+            if not cuda:
+                flat /= dist.get_world_size(self.group)
+            self.bytes_reduced += flat.numel() * flat.element_size()
+            off = 0
+            for b in self._small:
+                b.copy_(flat[off:off + b.numel()].view_as(b))
+                off += b.numel()
+        for w in self._pending:
+            if isinstance(w, tuple):
+                w[0].wait()
+                w[1].div_(dist.get_world_size(self.group))
+            else:
+                w.wait()
+        self._pending, self._small, self._seen = [], [], set()

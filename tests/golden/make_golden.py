@@ -175,44 +175,62 @@ def diffusion_goldens(ns2):
 
 
 def gradient_goldens(ns2):
-    """d(loss)/d(theta) of the reference in fp64 (uncond_small weights, the diffusion golden's latents/times/noise):
-    every parameter gradient's norm plus a few whole tensors — what the `-m gpu` backward test compares with."""
-    kwargs, B, N, _, _ = CASES["uncond_small"]
-    z = np.load(HERE / "diffusion_uncond_small.npz")
-    model = ns2.Model(**kwargs)
-    fill_module(model, seed=1234)
-    model = model.double()
-    diff = ns2.NaturalSpeech2(model=model, target_sample_hz=24000, timesteps=4)
-    latents = torch.from_numpy(z["latents"]).double()
-    times = torch.from_numpy(z["times"]).double()
-    noise = torch.from_numpy(z["noise"]).double()
-    # ns2.py:1621-1666 with the recorded draws
-    gamma = diff.gamma_schedule(times)
-    alpha, sigma = ns2.gamma_to_alpha_sigma(gamma[:, None, None], diff.scale)
-    noised = alpha * latents + sigma * noise
-    pred = model(noised, times)
-    target = alpha * noise - sigma * latents
-    loss = ((pred - target) ** 2).reshape(B, -1).mean(dim=1)
-    snr = (alpha * alpha) / (sigma * sigma)
-    weight = snr.clamp(max=diff.min_snr_gamma) / (snr + 1)
-    loss = (loss * weight).mean()
-    loss.backward()
-    out = {"loss": np.array(loss.item())}
-    keep = ("transformer.to_pred.1.weight", "transformer.layers.0.1.to_q.weight", "transformer.layers.1.5.2.1.weight",
-            "transformer.layers.0.5.0.bias", "transformer.layers.1.4.to_gamma_beta.weight", "wavenet.init_conv.weight",
-            "wavenet.stacks.0.blocks.2.conv.weight", "wavenet.stacks.1.blocks.0.skip_conv.weight",
-            "wavenet.stacks.1.blocks.1.to_time_cond.bias", "to_time_cond.1.weight", "to_time_cond.0.weights",
-            "transformer.to_pred.0.gamma", "wavenet.final_conv.bias")
-    names, norms = [], []
-    for n, p in model.named_parameters():
-        names.append(n)
-        norms.append(p.grad.norm().item())
-        if n in keep:
-            out["grad::" + n] = p.grad.numpy().astype(np.float32)
-    out["names"] = np.array(names)
-    out["norms"] = np.array(norms)
-    print(f"gradients: loss={loss.item():.6f} params={len(names)} total grad norm={np.sqrt((np.array(norms) ** 2).sum()):.4f}")
-    np.savez_compressed(HERE / "grads_uncond_small.npz", **out)
+    """d(loss)/d(theta) of the reference in fp64 (golden weights, the diffusion golden's latents/times/noise; the
+    conditional case adds the model golden's prompt / cond with cond_drop_prob = 0): every parameter gradient's norm
+    plus a few whole tensors — what the `-m gpu` backward tests compare with."""
+    keep = {
+        "uncond_small": ("transformer.to_pred.1.weight", "transformer.layers.0.1.to_q.weight",
+                         "transformer.layers.1.5.2.1.weight", "transformer.layers.0.5.0.bias",
+                         "transformer.layers.1.4.to_gamma_beta.weight", "wavenet.init_conv.weight",
+                         "wavenet.stacks.0.blocks.2.conv.weight", "wavenet.stacks.1.blocks.0.skip_conv.weight",
+                         "wavenet.stacks.1.blocks.1.to_time_cond.bias", "to_time_cond.1.weight", "to_time_cond.0.weights",
+                         "transformer.to_pred.0.gamma", "wavenet.final_conv.bias"),
+        "cond_small": ("transformer.layers.0.3.to_kv.weight", "transformer.layers.1.3.to_q.weight",
+                       "transformer.layers.0.2.to_gamma_beta.weight", "perceiver_resampler.latents",
+                       "perceiver_resampler.layers.0.0.to_kv.weight", "perceiver_resampler.layers.0.1.0.weight",
+                       "perceiver_resampler.proj_context.weight", "perceiver_resampler.norm.gamma",
+                       "cond_to_model_dim.weight", "to_prompt_cond.1.weight", "wavenet.init_conv.weight",
+                       "transformer.layers.1.1.to_kv.weight", "to_time_cond.1.weight"),
+    }
+    zd = np.load(HERE / "diffusion_uncond_small.npz")
+    for case in ("uncond_small", "cond_small"):
+        kwargs, B, N, _, _ = CASES[case]
+        model = ns2.Model(**kwargs)
+        fill_module(model, seed=1234)
+        model = model.double()
+        diff = ns2.NaturalSpeech2.__new__(ns2.NaturalSpeech2)   # only the schedule helpers are needed
+        latents = torch.from_numpy(zd["latents"]).double()
+        times = torch.from_numpy(zd["times"]).double()
+        noise = torch.from_numpy(zd["noise"]).double()
+        extra = {}
+        if kwargs.get("condition_on_prompt"):
+            zm = np.load(HERE / f"model_{case}.npz")
+            extra = dict(prompt=torch.from_numpy(zm["in_prompt"]).double(), cond=torch.from_numpy(zm["in_cond"]).double(),
+                         cond_drop_prob=0.)
+        # ns2.py:1621-1666 with the recorded draws (sigmoid schedule, objective v, min-SNR-5 weight)
+        gamma = ns2.sigmoid_schedule(times)
+        alpha, sigma = ns2.gamma_to_alpha_sigma(gamma[:, None, None], 1.)
+        noised = alpha * latents + sigma * noise
+        pred = model(noised, times, **extra)
+        target = alpha * noise - sigma * latents
+        loss = ((pred - target) ** 2).reshape(B, -1).mean(dim=1)
+        snr = (alpha * alpha) / (sigma * sigma)
+        weight = snr.clamp(max=5) / (snr + 1)
+        loss = (loss * weight).mean()
+        loss.backward()
+        out = {"loss": np.array(loss.item())}
+        names, norms = [], []
+        for n, p in model.named_parameters():
+            names.append(n)
+            g = p.grad if p.grad is not None else torch.zeros_like(p)
+            norms.append(g.norm().item())
+            if n in keep[case]:
+                out["grad::" + n] = g.numpy().astype(np.float32)
+        out["names"] = np.array(names)
+        out["norms"] = np.array(norms)
+        print(f"gradients[{case}]: loss={loss.item():.6f} params={len(names)} "
+              f"total grad norm={np.sqrt((np.array(norms) ** 2).sum()):.4f}")
+        np.savez_compressed(HERE / f"grads_{case}.npz", **out)
 
 
 def rvq_goldens():

@@ -130,6 +130,39 @@ def test_scalar_loss_allreduce_gloo_world2():
     assert res[0] == pytest.approx(expect) and res[1] == pytest.approx(expect)
 
 
+def _reducer_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    from naturalspeech2_pytorch_b200 import parallel
+    parallel.init_from_env(backend="gloo")
+    red = parallel.GradReducer(coalesce_below=1024)
+    big = torch.full((4, 512), float(rank + 1))            # 8 KB: its own (asynchronous) collective
+    small = torch.full((7,), float(10 * (rank + 1)))       # coalesced into the flat tail message
+    grads = {"a": big[:2], "b": big[2:], "c": small, "d": small[:3]}   # views of shared packed buffers
+    red.reduce_all(grads)
+    red.finish()
+    q.put((rank, float(big.mean()), float(small.mean()), red.bytes_reduced))
+    dist.destroy_process_group()
+
+
+def test_grad_reducer_averages_packed_buffers_gloo_world2():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_reducer_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for _, big, small, nbytes in res:
+        assert big == pytest.approx(1.5) and small == pytest.approx(15.0)
+        assert nbytes == 4 * 512 * 4 + 7 * 4       # every base buffer exactly once
+
+
 def test_rvq_empty_input_returns_empty_tensors():
     from naturalspeech2_pytorch_b200 import EncodecRVQ
     codec = EncodecRVQ(torch.randn(8, 1024, 128))
