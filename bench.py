@@ -342,6 +342,64 @@ def secondary_cfg3(dev, peaks):
             "step_frac_of_sustained_peak": round(tf / sus, 4)}
 
 
+def train_step_dp(dev, world, peaks, steps=4, warmup=2):
+    """configs[4]: conditioned diffusion TRAINING step (Model(512, depth 12, dim_prompt 512, condition_on_prompt) inside
+    NaturalSpeech2.forward -> loss.backward() -> fused AdamW), 32 samples per GPU, data parallel: gradient all-reduce
+    overlapped with the backward (parallel.GradReducer) + the scalar-loss all-reduce.  Runs on EVERY rank."""
+    import torch
+    import torch.distributed as dist
+    from naturalspeech2_pytorch_b200 import Model, NaturalSpeech2
+    from naturalspeech2_pytorch_b200.parallel import GradReducer, global_mean_loss
+    rank = int(os.environ.get("RANK", "0"))
+    torch.manual_seed(0)
+    model = Model(**CFG3).to(dev).train()
+    ns = NaturalSpeech2(model, target_sample_hz=24000)
+    if world > 1:
+        model.grad_reducer = GradReducer()
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-4, fused=True)
+    g = torch.Generator().manual_seed(100 + rank)
+    B = BATCH
+    lat = torch.randn(B, SEQ, 512, generator=g).to(dev)
+    prompt = torch.randn(B, 103, 512, generator=g).to(dev)
+    cond = torch.randn(B, 512, SEQ, generator=g).to(dev)
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        loss = ns(lat, prompt_enc=prompt, cond=cond)
+        loss.backward()
+        opt.step()
+        return global_mean_loss(loss.detach(), B)
+
+    for _ in range(warmup):
+        step()
+    if world > 1:
+        dist.barrier(device_ids=[dev.index])
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        loss = step()
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item()) / steps
+    nbytes = model.grad_reducer.bytes_reduced // max(1, steps + warmup) if world > 1 else 0
+    flops = 3 * FLOPS_PER_SAMPLE_CFG3 * B * world
+    sus = float(peaks.get("bf16_tflops_sustained", 1400.0))
+    res = {"metric": "train-steps/sec", "unit": "steps/s", "value": round(1e3 / ms, 3), "ms_per_step": round(ms, 3),
+           "workload": "configs[4]: conditioned diffusion training step (cfg3 model, fwd + hand-written bwd + fused AdamW), "
+                       f"32 samples per GPU, global batch {B * world}, gradient all-reduce overlapped with the backward",
+           "n_gpus": world, "global_batch": B * world, "samples_per_s": round(B * world * 1e3 / ms, 1),
+           "loss": round(float(loss), 5), "grad_allreduce_bytes_per_step": int(nbytes),
+           "tflops_3x_forward": round(flops / (ms * 1e-3) / 1e12, 1),
+           "frac_of_sustained_peak_per_gpu": round(flops / world / (ms * 1e-3) / 1e12 / sus, 4)}
+    del opt, ns, model
+    torch.cuda.empty_cache()
+    return res
+
+
 # ------------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------------
@@ -506,9 +564,17 @@ def run_ours(args):
     d2h = out_host[0].numel() * 4
     model.use_cuda_graphs = False
 
+    # ------------------------------- configs[4]: data-parallel training step (all ranks) -------------
+    secondary = {}
+    if not args.no_secondary:
+        try:
+            secondary["train_cfg5"] = train_step_dp(dev, world, _peaks()[0])
+        except Exception as e:  # a secondary number must never take the headline line down
+            secondary["train_cfg5"] = {"error": f"{type(e).__name__}: {e}"}
+        barrier()
+
     # ------------------------------- roofline: the FFN conv GEMM inside real steps -------------------
     roof = parity = cpu_base = None
-    secondary = {}
     if rank == 0:
         model._prof = []
         for _ in range(3):
