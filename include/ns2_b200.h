@@ -258,14 +258,16 @@ int ns2_x_start(const float* x, const float* pred, const float* alpha, const flo
 /* ------------------------------------------------------------------------------------------------
  * 7. Residual vector quantisation (Encodec RVQ encode/decode; third-party code reached from
  *    ns2.py:1445,1611 via audiolm_pytorch.EncodecWrapper -> encodec ResidualVectorQuantizer).
- *    ns2_rvq_prepare : codebooks f32 (Q, K, d) -> fp16 copy (Q, K, d) scaled by 2^-e_q, ||c||^2 f32 (Q, K),
- *                      meta f32 (Q, 2) = {max_k ||c_k||, 2^e_q}
+ *    ns2_rvq_prepare : codebooks f32 (Q, K, d) -> cb_f16: NS2_RVQ_PREPARED_HALFS(Q, K, d) fp16 values = the copy
+ *                      (Q, K, d) scaled by 2^-e_q followed by the (Q, K, 16) norm blocks (||c||^2 as an fp16 hi/lo pair,
+ *                      laid out for the tensor core); ||c||^2 f32 (Q, K); meta f32 (Q, 2) = {max_k ||c_k||, 2^e_q}
  *    ns2_rvq_encode  : frames f32 (F, d) -> codes int64 (F, Q); residual chain in fp32, nearest
  *                      codeword by exact squared L2 distance, ties -> lowest index.  d must be 128,
  *                      K a multiple of 128.
  *    ns2_rvq_decode  : emb f32 (F, d) = sum_q codebooks[q, codes[f,q], :]  (summed in order q = 0..Q-1)
  * ------------------------------------------------------------------------------------------------ */
-#define NS2_RVQ_STATS_LEN 4
+#define NS2_RVQ_PREPARED_HALFS(q, k, d) ((long long)(q) * (k) * ((d) + 16))
+#define NS2_RVQ_STATS_LEN 260  /* 4 counters + 32 stages x 8 clock64 stamps of CTA 0 (bring-up timeline) */
 int ns2_rvq_prepare(const float* codebooks, int32_t q, int32_t k, int32_t d, void* cb_f16,
                     float* cb_norm2, float* cb_meta, ns2_stream_t stream);
 int ns2_rvq_encode(const float* frames, int64_t num_frames, int32_t d, const float* codebooks,

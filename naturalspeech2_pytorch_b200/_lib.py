@@ -14,7 +14,7 @@ NS2_EPI_BF16, NS2_EPI_F32, NS2_EPI_GEGLU, NS2_EPI_WAVENET = 0, 1, 2, 3
 NS2_GEMM_MAX_SEGS = 8
 NS2_GEMM_MAX_GROUPS = 8
 NS2_MSE_SCRATCH_PER_SAMPLE = 64
-NS2_RVQ_STATS_LEN = 4
+NS2_RVQ_STATS_LEN = 260
 NS2_OBJ_V, NS2_OBJ_EPS, NS2_OBJ_X0 = 0, 1, 2
 NS2_ABI_VERSION = 2
 

@@ -74,6 +74,22 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   }
 }
 
+// Same bounded wait for service warps that idle through long phases of their CTA: sleeping between polls leaves the
+// issue slots of their SM sub-partition to the compute warps (+2 % on the RVQ kernel).
+__device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity, unsigned ns) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  uint32_t it = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(ns);
+    if (((++it) & 0xfff) == 0 && (clock64() - t0) > 2000000000LL) {
+      printf("ns2: mbarrier wait timed out (block %d thread %d bar 0x%x parity %u)\n", blockIdx.x,
+             threadIdx.x, bar, parity);
+      __trap();
+    }
+  }
+}
+
 // generic-proxy smem writes -> visible to the async proxy (TMA / tcgen05.mma operand reads)
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -123,6 +139,13 @@ __device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* m, uint32_t
                "r"(src), "r"(c0), "r"(c1)
                : "memory");
 }
+// plain 1-D bulk copy global -> shared (16-byte aligned, size % 16 == 0), completion on an mbarrier like the tensor loads
+__device__ __forceinline__ void bulk_load_1d(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t mbar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
+               "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(mbar)
+               : "memory");
+}
+
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void tma_store_wait_read() {  // smem of all but the N newest groups may be reused
@@ -322,6 +345,17 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr, uint32_t
   d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
   d |= static_cast<uint64_t>(1) << 46;
   d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+
+// Un-swizzled ("interleave") K-major operand: 8-row x 16-byte core matrices, LBO = distance between the two K halves of a
+// 16-element K step, SBO = distance between consecutive 8-row groups (cute: ((8,m),(T,2)):((1T,SBO),(1,LBO))).
+__device__ __forceinline__ uint64_t umma_desc_plain(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
   return d;
 }
 

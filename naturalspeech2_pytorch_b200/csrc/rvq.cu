@@ -5,7 +5,10 @@
 //   for q in 0..Q-1:  idx = argmin_k ||r - C_q[k]||^2 (first minimum wins);  r -= C_q[idx]
 //
 // The distance contraction runs on tcgen05 tensor cores in fp16 (fp32 accumulate) as a *filter*:
-//   s~_k = ||c_k||^2 - 2 r.c_k     with a rigorous bound |s~_k - s_k| <= E = 2 * 1.05 * 2^-10 * ||r|| * max_k ||c_k||
+//   s~_k = ||c_k||^2 - 2 r.c_k     with a rigorous bound |s~_k - s_k| <= E = 2 * 1.05 * 2^-10 * ||r|| * max_k ||c_k|| + ...
+// The whole score comes out of the tensor core: besides the 128 latent dims the MMA contracts one extra K block that
+// carries ||c_k||^2 (split into an fp16 hi/lo pair, prepared once per codebook) against a per-row power of two, so
+// the accumulator holds D = s~ * 2^-(e+ex+1) and the scan is pure compare/select work (no FMA, no ||c||^2 table).
 // Every code whose approximate score is within 2E of the approximate minimum is a candidate; candidates
 // are re-scored exactly in fp64 from the fp32 operands, so the emitted index is the exact argmin
 // (ties -> lowest index) — bit-exact against the fp64 oracle — while >99% of the flops stay on tensor cores.
@@ -15,8 +18,9 @@
 //              branch-free top-4 on packed (score|index) keys; fp32 residuals live in padded shared memory for all
 //              Q stages; the same threads build the fp16 A tile, re-score near-ties in fp64 (per lane, or
 //              warp-cooperatively for crowded 32-code blocks / bands) and subtract the chosen fp32 codeword
-//   warp 8     TMA producer: streams the fp16 codebooks (128 codes x 128 dims per chunk) through a 3-deep ring
-//   warp 9     tcgen05.mma issuer: D[128 frames x 128 codes] per chunk, double-buffered in TMEM
+//   warp 8     TMA producer: streams the fp16 codebooks (128 codes x 128 dims + the 4 KB norm block per chunk) through
+//              a 3-deep ring
+//   warp 9     tcgen05.mma issuer: D[128 frames x 128 codes] per chunk (8 + 1 MMAs), double-buffered in TMEM
 #include "ptx.cuh"
 #include "host_common.h"
 #include "../../include/ns2_b200.h"
@@ -38,14 +42,19 @@ constexpr int RSTRIDE = D + 4;        // floats per residual row: +4 keeps per-t
 constexpr int MAX_K = 2048;
 constexpr int OFF_A = 0;
 constexpr int OFF_B = OFF_A + A_BYTES;
-constexpr int OFF_R = OFF_B + RING * B_BYTES;        // fp32 residuals, row-major padded: 67.6 KB
-constexpr int OFF_CN2 = OFF_R + BF * RSTRIDE * 4;    // ||c||^2, double-buffered across stages (2 x 8 KB)
-constexpr int OFF_KEYS = OFF_CN2 + 2 * MAX_K * 4;    // top-8 keys of each column half: [half][row][8] floats (8 KB)
-constexpr int OFF_ROWP = OFF_KEYS + 2 * BF * 8 * 4;  // per-row {scale, dscale, E16, unused}
-constexpr int OFF_SEL = OFF_ROWP + BF * 4 * 4;       // chosen code per row (this stage)
-constexpr int OFF_CAND = OFF_SEL + BF * 4;           // per-warp candidate list of the row being re-scored
-constexpr int OFF_BAR = OFF_CAND + 8 * 16 * 4;
-constexpr int SMEM_BYTES = OFF_BAR + 256;
+constexpr int X_BYTES = 4096;         // norm block of one chunk / of the A tile: [16 row groups][2 K halves][8 rows][8 fp16]
+                                      // = the canonical un-swizzled K-major UMMA layout (SBO 256 B, LBO 128 B)
+constexpr int OFF_BX = OFF_B + RING * B_BYTES;       // norm blocks of the ring stages
+constexpr int OFF_AX = OFF_BX + RING * X_BYTES;      // per-row power of two (K half 0, elements 0 and 1), rest zero
+constexpr int OFF_R = OFF_AX + X_BYTES;              // fp32 residuals, row-major padded: 67.6 KB
+constexpr int OFF_KEYS = OFF_R + BF * RSTRIDE * 4;   // top-8 keys of each column half: [half][row][8] floats (8 KB)
+constexpr int OFF_ROWP = OFF_KEYS + 2 * BF * 8 * 4;  // per-row {scale, unused, error bound in D units, force-exact flag}
+constexpr int OFF_SEL = OFF_ROWP + BF * 4 * 4;       // (unused)
+constexpr int OFF_CAND = OFF_SEL + BF * 4;           // CTA-wide queue of the rows that need the exact re-score
+constexpr int OFF_BAR = OFF_CAND + (4 + BF) * 4;     // queue of ambiguous rows: [count, pad x3, BF entries]
+constexpr int OFF_META = OFF_BAR + 256;             // per-stage {max ||c||, 2^e} of the first 32 stages
+constexpr int OFF_TL = OFF_META + 256;               // bring-up timeline of CTA 0: 32 stages x 8 clock64 stamps
+constexpr int SMEM_BYTES = OFF_TL + 2048;
 constexpr int TMEM_COLS = 256;
 constexpr int SCAN_THREADS = 256;     // warps 0-7: quarter = warp & 3 (TMEM lanes), column half = warp >> 2
 }  // namespace rvq
@@ -54,7 +63,7 @@ struct RvqDev {
   CUtensorMap tmB;            // fp16 codebooks viewed as (Q*K rows, 128 cols)
   const float* frames;        // (F, 128)
   const float* codebooks;     // (Q, K, 128) fp32
-  const float* cn2;           // (Q, K)
+  const __half* cbx;          // (Q, K/128, 2048) fp16 norm blocks (behind the fp16 codebooks in the prepared buffer)
   const float* meta;          // (Q, 2): max ||c||, 2^e_q
   long long* codes;           // (F, Q)
   unsigned long long* stats;  // optional: [0] lookups, [1] near-ties re-scored, [2] full scans, [3] sub-chunk scans
@@ -102,6 +111,12 @@ __device__ __forceinline__ double coop_reduce(const float4 r, const float4 v) {
   return a;
 }
 
+// bring-up timeline: stats[4 + q*8 + slot] = clock64 of CTA 0 (tools/rvq_timeline.py); q < 32
+#define NS2_RVQ_STAMP(slot)                                                                              \
+  do {                                                                                                   \
+    if (p.stats != nullptr && blockIdx.x == 0 && q < 32) tl_s[q * 8 + (slot)] = clock64();               \
+  } while (0)
+
 __device__ __forceinline__ void scan_barrier() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 // sorted insert of a key into the ascending 4-tuple (g0..g3): 7 min/max, no branches
@@ -123,6 +138,13 @@ __device__ __forceinline__ void insert8(float key, float (&g)[8]) {
     g[i] = lo;
   }
   g[7] = fminf(g[7], t);
+}
+
+// packed key of one score: low 5 mantissa bits replaced by the column index, as ONE LOP3 ((a & b) | c = LUT 0xEA)
+__device__ __forceinline__ uint32_t key5(uint32_t score_bits, uint32_t idx) {
+  uint32_t k;
+  asm("lop3.b32 %0, %1, 0xFFFFFFE0, %2, 0xEA;" : "=r"(k) : "r"(score_bits), "r"(idx));
+  return k;
 }
 
 // (distance, index) lexicographic minimum across the warp
@@ -148,11 +170,12 @@ __global__ void __launch_bounds__(320, 1) rvq_encode_kernel(const __grid_constan
     __trap();
   }
   float* R = reinterpret_cast<float*>(smem + OFF_R);
-  float* cn2_s = reinterpret_cast<float*>(smem + OFF_CN2);
   float* keys_s = reinterpret_cast<float*>(smem + OFF_KEYS);
   float4* rowp_s = reinterpret_cast<float4*>(smem + OFF_ROWP);
-  int* sel_s = reinterpret_cast<int*>(smem + OFF_SEL);
-  int* cand_s = reinterpret_cast<int*>(smem + OFF_CAND);
+  int* queue_s = reinterpret_cast<int*>(smem + OFF_CAND);   // [0] = count, [1 + i] = row | na << 8 | nb << 12 | force << 16
+  float* meta_s = reinterpret_cast<float*>(smem + OFF_META);
+  long long* tl_s = reinterpret_cast<long long*>(smem + OFF_TL);   // stamps stay in smem until the end: no global
+                                                                   // stores inside the measured phases
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
   uint64_t* b_full = bars + 0;    // [RING]
   uint64_t* b_empty = bars + 3;   // [RING]
@@ -191,13 +214,15 @@ __global__ void __launch_bounds__(320, 1) rvq_encode_kernel(const __grid_constan
       for (int q = 0; q < p.Q; ++q) {
         for (int c = 0; c < chunks; ++c, ++it) {
           const uint32_t st = it % RING, ph = (it / RING) & 1;
-          mbar_wait(smem_u32(&b_empty[st]), ph ^ 1);
+          mbar_wait_backoff(smem_u32(&b_empty[st]), ph ^ 1, 200);
           const uint32_t fb = smem_u32(&b_full[st]);
-          mbar_arrive_expect_tx(fb, B_BYTES);
+          mbar_arrive_expect_tx(fb, B_BYTES + X_BYTES);
           const uint32_t dst = smem_u32(smem + OFF_B + st * B_BYTES);
           const int row0 = q * p.K + c * BC;
           tma_load_2d(dst, &p.tmB, fb, 0, row0);
           tma_load_2d(dst + BC * 128, &p.tmB, fb, 64, row0);
+          bulk_load_1d(smem_u32(smem + OFF_BX + st * X_BYTES),
+                       p.cbx + (static_cast<long long>(q) * chunks + c) * (X_BYTES / 2), X_BYTES, fb);
         }
       }
     }
@@ -208,7 +233,7 @@ __global__ void __launch_bounds__(320, 1) rvq_encode_kernel(const __grid_constan
       const uint32_t abase = smem_u32(smem + OFF_A);
       uint32_t it = 0;
       for (int q = 0; q < p.Q; ++q) {
-        mbar_wait(smem_u32(a_full), q & 1);
+        mbar_wait_backoff(smem_u32(a_full), q & 1, 100);
         tc_fence_after();
         for (int c = 0; c < chunks; ++c, ++it) {
           const uint32_t st = it % RING, ph = (it / RING) & 1;
@@ -223,6 +248,9 @@ __global__ void __launch_bounds__(320, 1) rvq_encode_kernel(const __grid_constan
             tc_mma_f16(tmem_base + buf * BC, umma_desc_sw128(abase + off, 16, 1024),
                        umma_desc_sw128(bbase + off, 16, 1024), idesc, k > 0);
           }
+          // + 2^(e-ex+6) * (hi_k + lo_k) = ||c_k||^2 * 2^-(e+ex+1): the norm term of the score
+          tc_mma_f16(tmem_base + buf * BC, umma_desc_plain(smem_u32(smem + OFF_AX), 128, 256),
+                     umma_desc_plain(smem_u32(smem + OFF_BX + st * X_BYTES), 128, 256), idesc, 1);
           tc_commit(smem_u32(&b_empty[st]));
           tc_commit(smem_u32(&d_full[buf]));
         }
@@ -233,9 +261,9 @@ __global__ void __launch_bounds__(320, 1) rvq_encode_kernel(const __grid_constan
     const int quarter = warp & 3, half = warp >> 2;
     const int row = quarter * 32 + lane;       // frame owned (together with the thread of the other half)
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
-    float* rrow = R + row * RSTRIDE;
 
-    // cooperative, coalesced load of the 128 frames: warp w fills rows [16w, 16w+16); stage-0 row parameters
+    float* rrow = R + row * RSTRIDE;
+    // cooperative, coalesced load of the 128 frames: warp w fills rows [16w, 16w+16)
     {
 #pragma unroll 4
       for (int r = warp * 16; r < warp * 16 + 16; ++r) {
@@ -244,18 +272,24 @@ __global__ void __launch_bounds__(320, 1) rvq_encode_kernel(const __grid_constan
         if (fr < p.num_frames) v = __ldg(reinterpret_cast<const float4*>(p.frames + fr * D) + lane);
         reinterpret_cast<float4*>(R + r * RSTRIDE)[lane] = v;
       }
-      for (int i = threadIdx.x; i < p.K; i += SCAN_THREADS) cn2_s[i] = __ldg(p.cn2 + i);
+      for (int i = threadIdx.x; i < X_BYTES / 16; i += SCAN_THREADS)
+        reinterpret_cast<uint4*>(smem + OFF_AX)[i] = make_uint4(0u, 0u, 0u, 0u);
+      if (threadIdx.x < 64 && threadIdx.x < 2 * p.Q) meta_s[threadIdx.x] = __ldg(p.meta + threadIdx.x);
     }
     unsigned long long n_ambig = 0, n_full = 0, n_sub = 0;
     uint32_t it = 0;
     for (int q = 0; q < p.Q; ++q) {
-      scan_barrier();  // [B1] residuals and ||c||^2 of this stage are in place
-      const float* cn2q = cn2_s + (q & 1) * MAX_K;
+      scan_barrier();  // [B1] residuals of this stage are in place
+      if (threadIdx.x == 0) {
+        queue_s[0] = 0;   // filled after [B2]; the previous stage's last read was before [B1]
+        NS2_RVQ_STAMP(0);
+      }
       // row scale (exact power of two into fp16 range), |r|^2 and the filter margin; both threads of a row compute
       // them redundantly from the same data in the same order (bit-identical), so no exchange is needed
-      float4 rp;
+      float xs_row;
       {
-        const float cmax = __ldg(p.meta + 2 * q), cscale = __ldg(p.meta + 2 * q + 1);
+        const float cmax = q < 32 ? meta_s[2 * q] : __ldg(p.meta + 2 * q);
+        const float cscale = q < 32 ? meta_s[2 * q + 1] : __ldg(p.meta + 2 * q + 1);
         float amax = 0.f, ss = 0.f;
 #pragma unroll 8
         for (int i = 0; i < D / 4; ++i) {
@@ -265,16 +299,31 @@ __global__ void __launch_bounds__(320, 1) rvq_encode_kernel(const __grid_constan
         }
         int ex = 0;
         if (amax > 0.f) (void)frexpf(amax, &ex);          // amax = m * 2^ex, m in [0.5, 1)
-        const float xs = ldexpf(1.0f, -ex);
-        const float dscale = -2.0f * ldexpf(cscale, ex);  // s~ = cn2 + dscale * dot'
-        // |s~_k - s_k| <= E16 = 2 * 1.05 * 2^-10 * ||r|| * max||c||  (fp16 operand rounding, fp32 accumulate)
-        const float e16 = 2.0f * 0.001026f * sqrtf(ss) * 1.001f * cmax;
-        rp = make_float4(xs, dscale, e16, ss);
-        if (half == 0) rowp_s[row] = rp;   // read by the decision warps after [B2]
+        int es = 0;
+        (void)frexpf(cscale, &es);                        // cscale = 2^(es-1) exactly
+        const int e = es - 1;
+        xs_row = ldexpf(1.0f, -ex);
+        if (half == 0) {
+          // accumulator D = -sum (r xs)(c / 2^e) + ax * (hi + lo) = s~ * kinv,  kinv = 2^-(e+ex+1),  ax = 2^(e-ex+6)
+          // (hi + lo = ||c||^2 * 2^-(2e+7)).  ax must be a normal fp16; otherwise (residual 2^9 x smaller or 2^20 x
+          // larger than the codebook scale) the row skips the filter and is scanned exactly.
+          const int axe = e - ex + 6;
+          const bool force = axe < -14 || axe > 15;
+          const float ax = force ? 0.f : ldexpf(1.0f, axe);
+          const float kinv = ldexpf(1.0f, -(e + ex + 1));
+          // |D_k - s_k kinv| <= ED: fp16 operand rounding of the dot (2 * 1.05 * 2^-10 ||r|| max||c||), the hi/lo split
+          // of ||c||^2 (2^-23 of its fp16-scaled range = 2^-16 * 4^e), and fp32 accumulation of 9 K blocks (2^-20 of
+          // the largest partial sum, 128 + max||c||^2 kinv)
+          const float ed = (2.0f * 0.001026f * sqrtf(ss) * 1.001f * cmax + 1.53e-5f * cscale * cscale) * kinv +
+                           9.6e-7f * (128.0f + cmax * cmax * kinv);
+          rowp_s[row] = make_float4(xs_row, 0.f, ed, force ? 1.f : 0.f);   // read by the classification after [B2]
+          const uint32_t axx = static_cast<uint32_t>(__half_as_ushort(__float2half_rn(ax))) * 0x00010001u;
+          *reinterpret_cast<uint32_t*>(smem + OFF_AX + (row >> 3) * 256 + (row & 7) * 16) = axx;   // K elements 0, 1
+        }
       }
       // ---- fp16 A tile: this thread converts dims [64*half, 64*half + 64) of its row into atom `half` ----
       {
-        const float xs = rp.x;
+        const float xs = -xs_row;   // the tile holds -r * xs: the accumulator is then an ascending score
         uint8_t* arow = smem + OFF_A + half * (BF * 128) + row * 128;
         const float4* src = reinterpret_cast<const float4*>(rrow + half * 64);
 #pragma unroll
@@ -289,76 +338,86 @@ __global__ void __launch_bounds__(320, 1) rvq_encode_kernel(const __grid_constan
       }
       fence_proxy_async_smem();
       mbar_arrive(smem_u32(a_full));
-      // prefetch ||c||^2 of the next stage into registers (stored to the other buffer after the scan)
-      float cn_next[MAX_K / SCAN_THREADS];
-      if (q + 1 < p.Q) {
-#pragma unroll
-        for (int u = 0; u < MAX_K / SCAN_THREADS; ++u) {
-          const int i = threadIdx.x + u * SCAN_THREADS;
-          cn_next[u] = (i < p.K) ? __ldg(p.cn2 + (q + 1) * p.K + i) : 0.f;
-        }
-      }
+      if (threadIdx.x == 0) NS2_RVQ_STAMP(1);
 
       // ---- scan this thread's 64 columns of every 128-code chunk: branch-free top-8 on packed keys ----
-      const float dscale = rp.y;
+      // The accumulator already is the (scaled) score, so a key is one LOP3: (bits & ~31) | index.  The two 32-column
+      // TMEM loads of a chunk are software-pipelined against the compare/select work, and the accumulator buffer is
+      // handed back to the MMA warp as soon as its last column sits in registers.
       float g[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) g[i] = INFINITY;
-      for (int c = 0; c < chunks; ++c, ++it) {
-        const uint32_t buf = it & 1, dph = (it >> 1) & 1;
-        mbar_wait(smem_u32(&d_full[buf]), dph);
-        tc_fence_after();
-#pragma unroll 1
-        for (int sub = 0; sub < 2; ++sub) {
-          uint32_t v[32];
-          tmem_ld32(lane_addr + buf * BC + half * 64 + sub * 32, v);
-          tmem_ld_wait();
-          const int sub_id = c * 4 + half * 2 + sub;   // 32-code block index: code = sub_id * 32 + i
-          const float* cn = cn2q + sub_id * 32;
-          // local top-2 of the 32 scores, index i in the low 5 bits; two interleaved trackers for ILP
-          float a0 = INFINITY, a1 = INFINITY, b0 = INFINITY, b1 = INFINITY;
+      auto scan32 = [&](const uint32_t (&v)[32], int sub_id) {
+        // local top-2 of the 32 scores, index i in the low 5 bits.  FMNMX / LOP3 share the half-rate ALU pipe, which
+        // bounds this loop: a tracker (a0 <= a1) absorbs a PAIR of keys in 5 min/max (2.5 per key instead of 3):
+        //   m = min(k0,k1), M = max(k0,k1);  a1' = min3(a1, max(a0, m), M);  a0' = min(a0, m).   Two trackers for ILP.
+        float a0 = INFINITY, a1 = INFINITY, b0 = INFINITY, b1 = INFINITY;
 #pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            const float s0 = fmaf(dscale, __uint_as_float(v[i]), cn[i]);
-            const float s1 = fmaf(dscale, __uint_as_float(v[i + 1]), cn[i + 1]);
-            const float k0 = __uint_as_float((__float_as_uint(s0) & 0xFFFFFFE0u) | static_cast<uint32_t>(i));
-            const float k1 = __uint_as_float((__float_as_uint(s1) & 0xFFFFFFE0u) | static_cast<uint32_t>(i + 1));
-            float t = fmaxf(a0, k0); a0 = fminf(a0, k0); a1 = fminf(a1, t);
-            t = fmaxf(b0, k1); b0 = fminf(b0, k1); b1 = fminf(b1, t);
-          }
-          const float l0 = fminf(a0, b0);
-          const float l1 = fminf(fmaxf(a0, b0), fminf(a1, b1));
-          // widen the index field to 11 bits (block id above the 5 local bits) and merge into the global top-8
-          const uint32_t blk = static_cast<uint32_t>(sub_id) << 5;
-          insert8(__uint_as_float((__float_as_uint(l0) & 0xFFFFF81Fu) | blk), g);
-          insert8(__uint_as_float((__float_as_uint(l1) & 0xFFFFF81Fu) | blk), g);
+        for (int i = 0; i < 32; i += 4) {
+          const float k0 = __uint_as_float(key5(v[i], static_cast<uint32_t>(i)));
+          const float k1 = __uint_as_float(key5(v[i + 1], static_cast<uint32_t>(i + 1)));
+          const float k2 = __uint_as_float(key5(v[i + 2], static_cast<uint32_t>(i + 2)));
+          const float k3 = __uint_as_float(key5(v[i + 3], static_cast<uint32_t>(i + 3)));
+          const float m0 = fminf(k0, k1), M0 = fmaxf(k0, k1);
+          const float m1 = fminf(k2, k3), M1 = fmaxf(k2, k3);
+          a1 = fminf(fminf(a1, fmaxf(a0, m0)), M0);
+          a0 = fminf(a0, m0);
+          b1 = fminf(fminf(b1, fmaxf(b0, m1)), M1);
+          b0 = fminf(b0, m1);
         }
-        tc_fence_before();
-        mbar_arrive(smem_u32(&d_empty[buf]));
+        const float l0 = fminf(a0, b0);
+        const float l1 = fminf(fmaxf(a0, b0), fminf(a1, b1));
+        // widen the index field to 11 bits (block id above the 5 local bits) and merge into the global top-8
+        const uint32_t blk = static_cast<uint32_t>(sub_id) << 5;
+        insert8(__uint_as_float((__float_as_uint(l0) & 0xFFFFF81Fu) | blk), g);
+        insert8(__uint_as_float((__float_as_uint(l1) & 0xFFFFF81Fu) | blk), g);
+      };
+      {
+        uint32_t v0[32], v1[32];
+        mbar_wait(smem_u32(&d_full[it & 1]), (it >> 1) & 1);
+        tc_fence_after();
+        tmem_ld32(lane_addr + (it & 1) * BC + half * 64, v0);
+#pragma unroll 1
+        for (int c = 0; c < chunks; ++c, ++it) {
+          const uint32_t buf = it & 1;
+          tmem_ld_wait();                                              // v0 = columns [0, 32) of this chunk
+          tmem_ld32(lane_addr + buf * BC + half * 64 + 32, v1);
+          scan32(v0, c * 4 + half * 2);                                // code = sub_id * 32 + i
+          tmem_ld_wait();                                              // v1 = columns [32, 64)
+          tc_fence_before();
+          mbar_arrive(smem_u32(&d_empty[buf]));                        // every TMEM read of this buffer is complete
+          if (c + 1 < chunks) {
+            const uint32_t nit = it + 1;
+            mbar_wait(smem_u32(&d_full[nit & 1]), (nit >> 1) & 1);
+            tc_fence_after();
+            tmem_ld32(lane_addr + (nit & 1) * BC + half * 64, v0);
+          }
+          scan32(v1, c * 4 + half * 2 + 1);
+        }
       }
       {
         float4* kd = reinterpret_cast<float4*>(keys_s + (half * BF + row) * 8);
         kd[0] = make_float4(g[0], g[1], g[2], g[3]);
         kd[1] = make_float4(g[4], g[5], g[6], g[7]);
       }
-      if (q + 1 < p.Q) {
-        float* cnw = cn2_s + ((q + 1) & 1) * MAX_K;
-#pragma unroll
-        for (int u = 0; u < MAX_K / SCAN_THREADS; ++u) {
-          const int i = threadIdx.x + u * SCAN_THREADS;
-          if (i < p.K) cnw[i] = cn_next[u];
-        }
-      }
+      if (threadIdx.x == 0) NS2_RVQ_STAMP(2);
       scan_barrier();  // [B2] both halves' key lists are published
+      if (threadIdx.x == 0) NS2_RVQ_STAMP(3);
 
-      // ---- exact decision: warp w owns rows [16w, 16w+16) ----
+      // ---- exact decision + residual update ----
       // Candidates = every code whose key is within the error band of the best key.  Each column half keeps its own
       // sorted top-8; a band member can only be missing from the two lists if a list is entirely inside the band
       // (-> exact scan of the whole codebook) or if it was 3rd+ inside its 32-code block, in which case two better
       // band members share that block (-> that block is scanned exactly).
+      // Step 1: warp w classifies rows [16w, 16w+16) (lanes 0..15, one row each) and appends the ambiguous ones (~9 %)
+      //         to a CTA-wide queue.
+      // Step 2: it subtracts the exact fp32 codeword (same op as the reference) from its unambiguous rows, all 16
+      //         coalesced 512-byte codeword loads in flight at once.
+      // Step 3 (after [B3]): the 8 warps drain the queue round-robin - fp64 re-score, then the subtraction with the
+      //         winner's codeword, which is still in registers - so the ambiguous rows cost ceil(n/8) rounds instead of
+      //         the worst warp's own count (measured: the slowest warp used to hold the CTA ~6k cycles per stage).
       const float* cbq = p.codebooks + static_cast<long long>(q) * p.K * D;
       {
-        // lanes 0..15 classify one row each (lanes 16..31 mirror them): band sizes of the two sorted lists
         const int myrow = warp * 16 + (lane & 15);
         float ka[8], kb[8];
         {
@@ -369,54 +428,72 @@ __global__ void __launch_bounds__(320, 1) rvq_encode_kernel(const __grid_constan
           kb[0] = y0.x; kb[1] = y0.y; kb[2] = y0.z; kb[3] = y0.w; kb[4] = y1.x; kb[5] = y1.y; kb[6] = y1.z; kb[7] = y1.w;
         }
         const float kmin = fminf(ka[0], kb[0]);
-        const float e16 = rowp_s[myrow].z;
+        const float4 rpm = rowp_s[myrow];
+        const float e16 = rpm.z;                                                    // filter error bound, key units
         const float etrunc = 0.000244140625f * 1.01f * (fabsf(kmin) + 2.0f * e16);  // 2^-12 key truncation
         const float lim = kmin + 2.0f * (e16 + etrunc);
+        const bool force = rpm.w != 0.f;   // the filter was skipped for this row (scale out of fp16 range)
         int na = 0, nb = 0;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           na += (ka[i] <= lim) ? 1 : 0;   // lists are sorted: the band is a prefix
           nb += (kb[i] <= lim) ? 1 : 0;
         }
-        if (lane < 16) sel_s[myrow] = __float_as_uint(kmin) & 0x7FF;
-        unsigned todo = __ballot_sync(0xffffffffu, lane < 16 && na + nb > 1);
-        int* cand = cand_s + warp * 16;
-#pragma unroll 1
-        while (todo) {
-          const int src = __ffs(todo) - 1;
-          todo &= todo - 1;
-          const int r = warp * 16 + src;
-          const int ca = __shfl_sync(0xffffffffu, na, src), cb = __shfl_sync(0xffffffffu, nb, src);
-          // the row's owner publishes its candidate indices: list a in cand[0..8), list b in cand[8..16)
-          if (lane == src) {
+        const int mysel = __float_as_uint(kmin) & 0x7FF;
+        const bool amb = na + nb > 1 || force;
+        const unsigned amb_mask = __ballot_sync(0xffffffffu, lane < 16 && amb);
+        if (lane < 16 && amb) {
+          const int slot = atomicAdd(queue_s, 1);
+          queue_s[1 + slot] = myrow | (na << 8) | (nb << 12) | (force ? (1 << 16) : 0);
+        }
+        // step 2
+        float4 cw[16];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-              cand[u] = __float_as_uint(ka[u]) & 0x7FF;
-              cand[8 + u] = __float_as_uint(kb[u]) & 0x7FF;
-            }
-          }
-          __syncwarp();
-          const float4 rv = reinterpret_cast<const float4*>(R + r * RSTRIDE)[lane];
+        for (int u = 0; u < 16; ++u) {
+          const int sel = __shfl_sync(0xffffffffu, mysel, u);
+          cw[u] = coop_load(cbq + static_cast<long long>(sel) * D, lane);
+          const int r = warp * 16 + u;
+          if (lane == 0 && !((amb_mask >> u) & 1u) && f0 + r < p.num_frames) p.codes[(f0 + r) * p.Q + q] = sel;
+        }
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+          if ((amb_mask >> u) & 1u) continue;   // warp-uniform
+          float4* dst = reinterpret_cast<float4*>(R + (warp * 16 + u) * RSTRIDE) + lane;
+          float4 v = *dst;
+          v.x -= cw[u].x; v.y -= cw[u].y; v.z -= cw[u].z; v.w -= cw[u].w;
+          *dst = v;
+        }
+      }
+      if (threadIdx.x == 0) NS2_RVQ_STAMP(4);
+      scan_barrier();  // [B3] the queue of ambiguous rows is complete
+      if (threadIdx.x == 0) NS2_RVQ_STAMP(6);
+      {
+        const int total_rows = queue_s[0];
+#pragma unroll 1
+        for (int e = warp; e < total_rows; e += 8) {
+          const int ent = queue_s[1 + e];
+          const int r = ent & 0xFF, ca = (ent >> 8) & 0xF, cb = (ent >> 12) & 0xF;
+          // lane l < 8 holds entry l of list a, lanes 8..15 entry l-8 of list b (code index in the low 11 key bits)
+          int mycand = 0;
+          if (lane < 16) mycand = __float_as_uint(keys_s[((lane >> 3) * BF + r) * 8 + (lane & 7)]) & 0x7FF;
+          const bool member = (lane < ca) || (lane >= 8 && lane < 8 + cb);
+          float4* rdst = reinterpret_cast<float4*>(R + r * RSTRIDE) + lane;
+          const float4 rv = *rdst;
           double dbest = INFINITY;
           int best = 0x7fffffff;
+          float4 cbest = make_float4(0.f, 0.f, 0.f, 0.f);   // this lane's 4 dims of the best codeword so far
           ++n_ambig;
-          // crowded 32-code block among the band members of one list? (blocks never span the two halves)
+          // crowded 32-code block: two band members with the same block id (a block never spans the column halves)
+          const unsigned same = __match_any_sync(0xffffffffu, member ? (mycand >> 5) : (0x10000 + lane));
+          const unsigned crowded = __ballot_sync(0xffffffffu, member && __popc(same) > 1);
           int blk = -1;
-          bool full = (ca >= 8) || (cb >= 8);
-#pragma unroll 1
-          for (int l = 0; l < 2; ++l) {
-            const int cnt = l ? cb : ca;
-#pragma unroll 1
-            for (int i = 0; i + 1 < cnt; ++i)
-#pragma unroll 1
-              for (int j = i + 1; j < cnt; ++j)
-                if ((cand[8 * l + i] >> 5) == (cand[8 * l + j] >> 5)) {
-                  full = full || (blk >= 0 && blk != (cand[8 * l + i] >> 5));
-                  blk = cand[8 * l + i] >> 5;
-                }
+          bool full = (ca >= 8) || (cb >= 8) || ((ent >> 16) & 1);
+          if (crowded) {
+            blk = __shfl_sync(0xffffffffu, mycand >> 5, __ffs(crowded) - 1);
+            // two different crowded blocks (astronomically rare): exact scan of the whole codebook
+            full = full || __ballot_sync(0xffffffffu, ((crowded >> lane) & 1u) && (mycand >> 5) != blk) != 0u;
           }
           if (full) {
-            // a whole list inside the band, or two crowded blocks (astronomically rare): exact scan of the codebook
             ++n_full;
 #pragma unroll 1
             for (int k0 = 0; k0 < p.K; k0 += 8) {
@@ -426,7 +503,7 @@ __global__ void __launch_bounds__(320, 1) rvq_encode_kernel(const __grid_constan
 #pragma unroll
               for (int u = 0; u < 8; ++u) {
                 const double dk = coop_reduce(rv, cv[u]);
-                if (dk < dbest) { dbest = dk; best = k0 + u; }
+                if (dk < dbest) { dbest = dk; best = k0 + u; cbest = cv[u]; }
               }
             }
           } else {
@@ -439,13 +516,16 @@ __global__ void __launch_bounds__(320, 1) rvq_encode_kernel(const __grid_constan
 #pragma unroll
               for (int u = 0; u < 4; ++u) {
                 const int t = u0 + u;
-                kx[u] = (t < total) ? cand[t < ca ? t : 8 + (t - ca)] : cand[0];
+                const int src = (t < total) ? (t < ca ? t : 8 + (t - ca)) : 0;
+                kx[u] = __shfl_sync(0xffffffffu, mycand, src);
                 cv[u] = coop_load(cbq + static_cast<long long>(kx[u]) * D, lane);
               }
 #pragma unroll
               for (int u = 0; u < 4; ++u) {
                 const double dk = coop_reduce(rv, cv[u]);
-                if (u0 + u < total && (dk < dbest || (dk == dbest && kx[u] < best))) { dbest = dk; best = kx[u]; }
+                if (u0 + u < total && (dk < dbest || (dk == dbest && kx[u] < best))) {
+                  dbest = dk; best = kx[u]; cbest = cv[u];
+                }
               }
             }
             if (blk >= 0) {
@@ -458,38 +538,16 @@ __global__ void __launch_bounds__(320, 1) rvq_encode_kernel(const __grid_constan
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
                   const double dk = coop_reduce(rv, c8[u]);
-                  if (dk < dbest || (dk == dbest && k0 + u < best)) { dbest = dk; best = k0 + u; }
+                  if (dk < dbest || (dk == dbest && k0 + u < best)) { dbest = dk; best = k0 + u; cbest = c8[u]; }
                 }
               }
             }
           }
-          if (lane == 0) sel_s[r] = best;
-          __syncwarp();
+          if (lane == 0 && f0 + r < p.num_frames) p.codes[(f0 + r) * p.Q + q] = best;
+          *rdst = make_float4(rv.x - cbest.x, rv.y - cbest.y, rv.z - cbest.z, rv.w - cbest.w);
         }
       }
-      __syncwarp();
-      // ---- residual update with the exact fp32 codeword (same op as the reference) for this warp's own 16 rows;
-      //      eight coalesced 512-byte codeword loads in flight ----
-      {
-#pragma unroll 1
-        for (int u0 = 0; u0 < 16; u0 += 8) {
-          float4 cw[8];
-#pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const int r = warp * 16 + u0 + u;
-            const int sel = sel_s[r];
-            cw[u] = coop_load(cbq + static_cast<long long>(sel) * D, lane);
-            if (lane == 0 && f0 + r < p.num_frames) p.codes[(f0 + r) * p.Q + q] = sel;
-          }
-#pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            float4* dst = reinterpret_cast<float4*>(R + (warp * 16 + u0 + u) * RSTRIDE) + lane;
-            float4 v = *dst;
-            v.x -= cw[u].x; v.y -= cw[u].y; v.z -= cw[u].z; v.w -= cw[u].w;
-            *dst = v;
-          }
-        }
-      }
+      if (threadIdx.x == 0) NS2_RVQ_STAMP(5);
     }
     if (p.stats != nullptr) {
       if (half == 0 && f0 + row < p.num_frames) atomicAdd(p.stats + 0, static_cast<unsigned long long>(p.Q));
@@ -503,6 +561,8 @@ __global__ void __launch_bounds__(320, 1) rvq_encode_kernel(const __grid_constan
 
   tc_fence_before();
   __syncthreads();
+  if (p.stats != nullptr && blockIdx.x == 0 && threadIdx.x < 256 && static_cast<int>(threadIdx.x) < p.Q * 8)
+    p.stats[4 + threadIdx.x] = tl_s[threadIdx.x];
   if (warp == 0) {
     tc_fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS);
@@ -510,10 +570,12 @@ __global__ void __launch_bounds__(320, 1) rvq_encode_kernel(const __grid_constan
 }
 
 // ------------------------------------------------------------------------------------------------
-// prepare: fp16 copy scaled by a per-quantiser power of two, ||c||^2, max ||c||
+// prepare: fp16 copy scaled by a per-quantiser power of two, ||c||^2, max ||c||, and the fp16 hi/lo norm blocks the
+// encode kernel contracts as a ninth K block (layout: rvq::X_BYTES per 128-code chunk, see OFF_BX)
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) rvq_prepare_kernel(const float* __restrict__ cb, int K, int D,
                                                           __half* __restrict__ cb16,
+                                                          __half* __restrict__ cbx,
                                                           float* __restrict__ cn2,
                                                           float* __restrict__ meta) {
   const int q = blockIdx.x;
@@ -548,6 +610,15 @@ __global__ void __launch_bounds__(256) rvq_prepare_kernel(const float* __restric
     }
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     if (lane == 0) cn2[q * K + k] = static_cast<float>(s);
+    // norm block: val = ||c||^2 / scale^2 / 128 in [0, 1] as hi + lo (elements 0, 1 of K half 0), everything else zero
+    {
+      const float val = static_cast<float>(s) * inv * inv * 0.0078125f;
+      const __half hi = __float2half_rn(val);
+      const __half lo = __float2half_rn(val - __half2float(hi));
+      __half* blk = cbx + (static_cast<long long>(q) * (K / 128) + k / 128) * 2048 + ((k & 127) >> 3) * 128 + (k & 7) * 8;
+      if (lane < 8) blk[lane] = lane == 0 ? hi : (lane == 1 ? lo : __float2half_rn(0.f));   // K half 0
+      else if (lane < 16) blk[64 + lane - 8] = __float2half_rn(0.f);                        // K half 1
+    }
     nmax = fmaxf(nmax, static_cast<float>(sqrt(s)) * 1.0001f);
   }
   __syncthreads();
@@ -592,8 +663,10 @@ int ns2_rvq_prepare(const float* codebooks, int32_t q, int32_t k, int32_t d, voi
                     float* cb_norm2, float* cb_meta, ns2_stream_t stream) {
   NS2_REQUIRE(codebooks && cb_f16 && cb_norm2 && cb_meta, "rvq_prepare: NULL pointer");
   NS2_REQUIRE(q > 0 && k > 0 && d == 128, "rvq_prepare: d must be 128 (got %d)", d);
+  NS2_REQUIRE(k % 128 == 0, "rvq_prepare: codebook size %d must be a multiple of 128", k);
+  __half* cb16 = reinterpret_cast<__half*>(cb_f16);
   rvq_prepare_kernel<<<q, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      codebooks, k, d, reinterpret_cast<__half*>(cb_f16), cb_norm2, cb_meta);
+      codebooks, k, d, cb16, cb16 + static_cast<long long>(q) * k * d, cb_norm2, cb_meta);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   NS2_CUDA_CHECK(cudaGetLastError());
   return kOk;
@@ -619,18 +692,17 @@ int ns2_rvq_encode(const float* frames, int64_t num_frames, int32_t d, const flo
   if (rc != kOk) return rc;
   dev.frames = frames;
   dev.codebooks = codebooks;
-  dev.cn2 = cb_norm2;
+  dev.cbx = reinterpret_cast<const __half*>(cb_f16) + static_cast<long long>(q) * k * d;
   dev.meta = cb_meta;
   dev.codes = reinterpret_cast<long long*>(codes);
   dev.stats = reinterpret_cast<unsigned long long*>(stats);
   dev.num_frames = num_frames;
   dev.Q = q;
   dev.K = k;
-  NS2_CUDA_CHECK(set_max_smem_once(rvq_encode_kernel, rvq::SMEM_BYTES));
   const long long grid = (num_frames + rvq::BF - 1) / rvq::BF;
   NS2_REQUIRE(grid <= 0x7fffffffLL, "rvq_encode: too many frames");
-  rvq_encode_kernel<<<static_cast<unsigned>(grid), 320, rvq::SMEM_BYTES,
-                      static_cast<cudaStream_t>(stream)>>>(dev);
+  NS2_CUDA_CHECK(set_max_smem_once(rvq_encode_kernel, rvq::SMEM_BYTES));
+  rvq_encode_kernel<<<static_cast<unsigned>(grid), 320, rvq::SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(dev);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   NS2_CUDA_CHECK(cudaGetLastError());
   return kOk;

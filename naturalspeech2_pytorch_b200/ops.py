@@ -413,7 +413,8 @@ def rvq_prepare(codebooks: torch.Tensor):
     _req(codebooks, torch.float32, "codebooks")
     cb = codebooks.contiguous()
     Q, K, D = cb.shape
-    cb16 = torch.empty((Q, K, D), device=cb.device, dtype=torch.float16)
+    # fp16 copy (Q, K, D) followed by the (Q, K, 16) norm blocks: NS2_RVQ_PREPARED_HALFS
+    cb16 = torch.empty((Q * K * (D + 16),), device=cb.device, dtype=torch.float16)
     cn2 = torch.empty((Q, K), device=cb.device, dtype=torch.float32)
     meta = torch.empty((Q, 2), device=cb.device, dtype=torch.float32)
     check(lib.ns2_rvq_prepare(cb.data_ptr(), Q, K, D, cb16.data_ptr(), cn2.data_ptr(), meta.data_ptr(),

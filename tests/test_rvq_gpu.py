@@ -4,6 +4,7 @@ import pytest
 import torch
 
 from helpers import GOLDEN
+from naturalspeech2_pytorch_b200 import _lib
 from param_fill import rvq_fixture_inputs
 
 pytestmark = pytest.mark.gpu
@@ -16,7 +17,7 @@ def test_rvq_matches_oracle_and_golden():
     cb, variants = rvq_fixture_inputs()
     codec = EncodecRVQ(cb).cuda()
     for name, frames in variants.items():
-        stats = torch.zeros(4, dtype=torch.int64, device="cuda")
+        stats = torch.zeros(_lib.NS2_RVQ_STATS_LEN, dtype=torch.int64, device="cuda")
         codes, emb = codec.quantize(frames.cuda(), stats=stats)
         codes = codes.cpu().numpy()
         oracle_codes = rvq_oracle.encode(frames.numpy(), cb.numpy())

@@ -47,7 +47,7 @@ def _report(name, got, ref, atol, rtol):
 
 def run_elementwise():
     import torch
-    from naturalspeech2_pytorch_b200 import ops
+    from naturalspeech2_pytorch_b200 import _lib, ops
     torch.manual_seed(0)
     dev = "cuda"
     ok = True
@@ -122,7 +122,7 @@ def _gemm_ref(a, w, bias=None):
 
 def run_gemm_plain():
     import torch
-    from naturalspeech2_pytorch_b200 import ops
+    from naturalspeech2_pytorch_b200 import _lib, ops
     torch.manual_seed(1)
     dev = "cuda"
     ok = True
@@ -175,7 +175,7 @@ def _conv_ref(x, w, bias, dil):
 
 def run_gemm_conv():
     import torch
-    from naturalspeech2_pytorch_b200 import ops
+    from naturalspeech2_pytorch_b200 import _lib, ops
     torch.manual_seed(2)
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
@@ -195,7 +195,7 @@ def run_gemm_conv():
 
 def run_gemm_fused():
     import torch
-    from naturalspeech2_pytorch_b200 import ops
+    from naturalspeech2_pytorch_b200 import _lib, ops
     torch.manual_seed(3)
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
@@ -256,7 +256,7 @@ def _attn_ref(q, k, v, B, H, Nq, inner):
 
 def run_attn():
     import torch
-    from naturalspeech2_pytorch_b200 import ops
+    from naturalspeech2_pytorch_b200 import _lib, ops
     torch.manual_seed(4)
     dev = "cuda"
     ok = True
@@ -314,7 +314,7 @@ def run_attn():
 
 def run_rvq():
     import torch
-    from naturalspeech2_pytorch_b200 import ops
+    from naturalspeech2_pytorch_b200 import _lib, ops
     torch.manual_seed(5)
     dev = "cuda"
     ok = True
@@ -324,7 +324,7 @@ def run_rvq():
         x = torch.randn(F, 128, device=dev) * scale
         x[:5] = cb[0, 7] + cb[1, 11]  # exact hits
         prep = ops.rvq_prepare(cb)
-        stats = torch.zeros(4, device=dev, dtype=torch.int64)
+        stats = torch.zeros(_lib.NS2_RVQ_STATS_LEN, device=dev, dtype=torch.int64)
         codes = ops.rvq_encode(x, cb, prep, stats=stats)
         torch.cuda.synchronize()
         # fp64 oracle of the residual chain (fp32 residual updates, as in the reference)
