@@ -627,7 +627,7 @@ def run_ours(args):
                     "d2h_bytes_per_step": d2h},
             "roofline": roof, "parity": parity, "cpu_baseline": cpu_base, "secondary": secondary or None,
         }
-        print(json.dumps(line), flush=True)
+        _emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -682,7 +682,17 @@ def run_reference(args):
             "cpu_baseline": {"value": round(value, 5), "unit": "steps/s", "cores": _host_threads(),
                              "kind": ref.kind, "sample": sample},
             "e2e": {"value": round(value, 5), "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    _emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def _emit(line: dict) -> None:
+    """The one JSON line of the contract, on the process's original stdout."""
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main():
@@ -697,6 +707,14 @@ def main():
     ap.add_argument("--ref-max-batch", type=int, default=BATCH,
                     help="reference arm: cap on the per-step sample batch (tests use 2)")
     args = ap.parse_args()
+    # The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner at the first
+    # collective, the reference prints a GPU notice at import): send file descriptor 1 to stderr for the whole run and
+    # keep a private handle on the real stdout for the final line.
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)              # C-level writers (NCCL)
+    sys.stdout = sys.stderr    # Python-level writers (the reference's import-time print)
     if args.impl == "reference":
         run_reference(args)
     else:

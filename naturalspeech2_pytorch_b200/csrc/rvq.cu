@@ -117,6 +117,25 @@ __device__ __forceinline__ double coop_reduce(const float4 r, const float4 v) {
     if (p.stats != nullptr && blockIdx.x == 0 && q < 32) tl_s[q * 8 + (slot)] = clock64();               \
   } while (0)
 
+// Half-warp variant: lane hl of a 16-lane half owns dims [8 hl, 8 hl + 8); fixed order, xor-butterfly inside the half
+// (equal inputs give bit-equal results); every lane of the half returns the full distance.
+__device__ __forceinline__ double half_reduce8(const float4 r0, const float4 r1, const float4 c0, const float4 c1) {
+  const double d0 = static_cast<double>(r0.x) - static_cast<double>(c0.x);
+  const double d1 = static_cast<double>(r0.y) - static_cast<double>(c0.y);
+  const double d2 = static_cast<double>(r0.z) - static_cast<double>(c0.z);
+  const double d3 = static_cast<double>(r0.w) - static_cast<double>(c0.w);
+  const double d4 = static_cast<double>(r1.x) - static_cast<double>(c1.x);
+  const double d5 = static_cast<double>(r1.y) - static_cast<double>(c1.y);
+  const double d6 = static_cast<double>(r1.z) - static_cast<double>(c1.z);
+  const double d7 = static_cast<double>(r1.w) - static_cast<double>(c1.w);
+  double a = fma(d0, d0, fma(d1, d1, fma(d2, d2, d3 * d3)));
+  const double b = fma(d4, d4, fma(d5, d5, fma(d6, d6, d7 * d7)));
+  a += b;
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+  return a;
+}
+
 __device__ __forceinline__ void scan_barrier() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 // sorted insert of a key into the ascending 4-tuple (g0..g3): 7 min/max, no branches
@@ -467,84 +486,138 @@ __global__ void __launch_bounds__(320, 1) rvq_encode_kernel(const __grid_constan
       if (threadIdx.x == 0) NS2_RVQ_STAMP(4);
       scan_barrier();  // [B3] the queue of ambiguous rows is complete
       if (threadIdx.x == 0) NS2_RVQ_STAMP(6);
+      // One row per HALF-warp (lane hl of a half owns dims [8 hl, 8 hl + 8)), so a warp resolves two queue rows per
+      // round in one instruction stream; the rare rows (crowded block / full scan / filter skipped) are redone by the
+      // whole warp with the general routine.
+      auto resolve_row_fullwarp = [&](int ent) {
+        const int r = ent & 0xFF, ca = (ent >> 8) & 0xF, cb = (ent >> 12) & 0xF;
+        // lane l < 8 holds entry l of list a, lanes 8..15 entry l-8 of list b (code index in the low 11 key bits)
+        int mycand = 0;
+        if (lane < 16) mycand = __float_as_uint(keys_s[((lane >> 3) * BF + r) * 8 + (lane & 7)]) & 0x7FF;
+        const bool member = (lane < ca) || (lane >= 8 && lane < 8 + cb);
+        float4* rdst = reinterpret_cast<float4*>(R + r * RSTRIDE) + lane;
+        const float4 rv = *rdst;
+        double dbest = INFINITY;
+        int best = 0x7fffffff;
+        float4 cbest = make_float4(0.f, 0.f, 0.f, 0.f);   // this lane's 4 dims of the best codeword so far
+        // crowded 32-code block: two band members with the same block id (a block never spans the column halves)
+        const unsigned same = __match_any_sync(0xffffffffu, member ? (mycand >> 5) : (0x10000 + lane));
+        const unsigned crowded = __ballot_sync(0xffffffffu, member && __popc(same) > 1);
+        int blk = -1;
+        bool full = (ca >= 8) || (cb >= 8) || ((ent >> 16) & 1);
+        if (crowded) {
+          blk = __shfl_sync(0xffffffffu, mycand >> 5, __ffs(crowded) - 1);
+          // two different crowded blocks (astronomically rare): exact scan of the whole codebook
+          full = full || __ballot_sync(0xffffffffu, ((crowded >> lane) & 1u) && (mycand >> 5) != blk) != 0u;
+        }
+        if (full) {
+          ++n_full;
+#pragma unroll 1
+          for (int k0 = 0; k0 < p.K; k0 += 8) {
+            float4 cv[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) cv[u] = coop_load(cbq + static_cast<long long>(k0 + u) * D, lane);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              const double dk = coop_reduce(rv, cv[u]);
+              if (dk < dbest) { dbest = dk; best = k0 + u; cbest = cv[u]; }
+            }
+          }
+        } else {
+          // band members of both lists, four codewords in flight at a time
+          const int total = ca + cb;
+#pragma unroll 1
+          for (int u0 = 0; u0 < total; u0 += 4) {
+            float4 cv[4];
+            int kx[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int t = u0 + u;
+              const int src = (t < total) ? (t < ca ? t : 8 + (t - ca)) : 0;
+              kx[u] = __shfl_sync(0xffffffffu, mycand, src);
+              cv[u] = coop_load(cbq + static_cast<long long>(kx[u]) * D, lane);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const double dk = coop_reduce(rv, cv[u]);
+              if (u0 + u < total && (dk < dbest || (dk == dbest && kx[u] < best))) {
+                dbest = dk; best = kx[u]; cbest = cv[u];
+              }
+            }
+          }
+          if (blk >= 0) {
+            ++n_sub;
+#pragma unroll 1
+            for (int k0 = blk * 32; k0 < blk * 32 + 32; k0 += 16) {   // 16 codewords (8 KB) in flight: 2 L2 round trips
+              float4 c8[16];
+#pragma unroll
+              for (int u = 0; u < 16; ++u) c8[u] = coop_load(cbq + static_cast<long long>(k0 + u) * D, lane);
+#pragma unroll
+              for (int u = 0; u < 16; ++u) {
+                const double dk = coop_reduce(rv, c8[u]);
+                if (dk < dbest || (dk == dbest && k0 + u < best)) { dbest = dk; best = k0 + u; cbest = c8[u]; }
+              }
+            }
+          }
+        }
+        if (lane == 0 && f0 + r < p.num_frames) p.codes[(f0 + r) * p.Q + q] = best;
+        *rdst = make_float4(rv.x - cbest.x, rv.y - cbest.y, rv.z - cbest.z, rv.w - cbest.w);
+      };
       {
         const int total_rows = queue_s[0];
+        const int h = lane >> 4, hl = lane & 15;
 #pragma unroll 1
-        for (int e = warp; e < total_rows; e += 8) {
-          const int ent = queue_s[1 + e];
+        for (int e0 = warp * 2; e0 < total_rows; e0 += 16) {
+          const int e = e0 + h;
+          const bool valid = e < total_rows;
+          const int ent = valid ? queue_s[1 + e] : 0;
           const int r = ent & 0xFF, ca = (ent >> 8) & 0xF, cb = (ent >> 12) & 0xF;
-          // lane l < 8 holds entry l of list a, lanes 8..15 entry l-8 of list b (code index in the low 11 key bits)
-          int mycand = 0;
-          if (lane < 16) mycand = __float_as_uint(keys_s[((lane >> 3) * BF + r) * 8 + (lane & 7)]) & 0x7FF;
-          const bool member = (lane < ca) || (lane >= 8 && lane < 8 + cb);
-          float4* rdst = reinterpret_cast<float4*>(R + r * RSTRIDE) + lane;
-          const float4 rv = *rdst;
+          // half-lane hl < 8 holds entry hl of list a, 8..15 entry hl-8 of list b (code index in the low 11 key bits)
+          const int mycand = valid ? (__float_as_uint(keys_s[((hl >> 3) * BF + r) * 8 + (hl & 7)]) & 0x7FF) : 0;
+          const bool member = valid && ((hl < ca) || (hl >= 8 && hl < 8 + cb));
+          float4* rdst = reinterpret_cast<float4*>(R + r * RSTRIDE) + 2 * hl;
+          const float4 rv0 = rdst[0], rv1 = rdst[1];
+          if (lane == 0) n_ambig += 1 + ((e0 + 1 < total_rows) ? 1 : 0);
+          // crowded 32-code block: two band members of one row with the same block id
+          const unsigned same = __match_any_sync(0xffffffffu, member ? ((h << 12) | (mycand >> 5)) : (0x10000 + lane));
+          const unsigned crowded = __ballot_sync(0xffffffffu, member && __popc(same) > 1);
+          const bool rare_me = valid && (ca >= 8 || cb >= 8 || ((ent >> 16) & 1) || ((crowded >> (16 * h)) & 0xFFFFu) != 0u);
+          const unsigned rare = __ballot_sync(0xffffffffu, rare_me);
+          const int total = (valid && !rare_me) ? ca + cb : 0;
+          const int tmax = max(__shfl_sync(0xffffffffu, total, 0), __shfl_sync(0xffffffffu, total, 16));
           double dbest = INFINITY;
           int best = 0x7fffffff;
-          float4 cbest = make_float4(0.f, 0.f, 0.f, 0.f);   // this lane's 4 dims of the best codeword so far
-          ++n_ambig;
-          // crowded 32-code block: two band members with the same block id (a block never spans the column halves)
-          const unsigned same = __match_any_sync(0xffffffffu, member ? (mycand >> 5) : (0x10000 + lane));
-          const unsigned crowded = __ballot_sync(0xffffffffu, member && __popc(same) > 1);
-          int blk = -1;
-          bool full = (ca >= 8) || (cb >= 8) || ((ent >> 16) & 1);
-          if (crowded) {
-            blk = __shfl_sync(0xffffffffu, mycand >> 5, __ffs(crowded) - 1);
-            // two different crowded blocks (astronomically rare): exact scan of the whole codebook
-            full = full || __ballot_sync(0xffffffffu, ((crowded >> lane) & 1u) && (mycand >> 5) != blk) != 0u;
-          }
-          if (full) {
-            ++n_full;
+          float4 cb0 = make_float4(0.f, 0.f, 0.f, 0.f), cb1 = cb0;   // this lane's 8 dims of the best codeword so far
 #pragma unroll 1
-            for (int k0 = 0; k0 < p.K; k0 += 8) {
-              float4 cv[8];
+          for (int u0 = 0; u0 < tmax; u0 += 4) {
+            float4 c0[4], c1[4];
+            int kx[4];
 #pragma unroll
-              for (int u = 0; u < 8; ++u) cv[u] = coop_load(cbq + static_cast<long long>(k0 + u) * D, lane);
-#pragma unroll
-              for (int u = 0; u < 8; ++u) {
-                const double dk = coop_reduce(rv, cv[u]);
-                if (dk < dbest) { dbest = dk; best = k0 + u; cbest = cv[u]; }
-              }
+            for (int u = 0; u < 4; ++u) {
+              const int t = u0 + u;
+              const int src = 16 * h + ((t < total) ? (t < ca ? t : 8 + (t - ca)) : 0);
+              kx[u] = __shfl_sync(0xffffffffu, mycand, src);
+              const float4* cp = reinterpret_cast<const float4*>(cbq + static_cast<long long>(kx[u]) * D) + 2 * hl;
+              c0[u] = __ldg(cp);
+              c1[u] = __ldg(cp + 1);
             }
-          } else {
-            // band members of both lists, four codewords in flight at a time
-            const int total = ca + cb;
-#pragma unroll 1
-            for (int u0 = 0; u0 < total; u0 += 4) {
-              float4 cv[4];
-              int kx[4];
 #pragma unroll
-              for (int u = 0; u < 4; ++u) {
-                const int t = u0 + u;
-                const int src = (t < total) ? (t < ca ? t : 8 + (t - ca)) : 0;
-                kx[u] = __shfl_sync(0xffffffffu, mycand, src);
-                cv[u] = coop_load(cbq + static_cast<long long>(kx[u]) * D, lane);
-              }
-#pragma unroll
-              for (int u = 0; u < 4; ++u) {
-                const double dk = coop_reduce(rv, cv[u]);
-                if (u0 + u < total && (dk < dbest || (dk == dbest && kx[u] < best))) {
-                  dbest = dk; best = kx[u]; cbest = cv[u];
-                }
-              }
-            }
-            if (blk >= 0) {
-              ++n_sub;
-#pragma unroll 1
-              for (int k0 = blk * 32; k0 < blk * 32 + 32; k0 += 8) {
-                float4 c8[8];
-#pragma unroll
-                for (int u = 0; u < 8; ++u) c8[u] = coop_load(cbq + static_cast<long long>(k0 + u) * D, lane);
-#pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                  const double dk = coop_reduce(rv, c8[u]);
-                  if (dk < dbest || (dk == dbest && k0 + u < best)) { dbest = dk; best = k0 + u; cbest = c8[u]; }
-                }
+            for (int u = 0; u < 4; ++u) {
+              const double dk = half_reduce8(rv0, rv1, c0[u], c1[u]);
+              if (u0 + u < total && (dk < dbest || (dk == dbest && kx[u] < best))) {
+                dbest = dk; best = kx[u]; cb0 = c0[u]; cb1 = c1[u];
               }
             }
           }
-          if (lane == 0 && f0 + r < p.num_frames) p.codes[(f0 + r) * p.Q + q] = best;
-          *rdst = make_float4(rv.x - cbest.x, rv.y - cbest.y, rv.z - cbest.z, rv.w - cbest.w);
+          if (valid && !rare_me) {
+            if (hl == 0 && f0 + r < p.num_frames) p.codes[(f0 + r) * p.Q + q] = best;
+            rdst[0] = make_float4(rv0.x - cb0.x, rv0.y - cb0.y, rv0.z - cb0.z, rv0.w - cb0.w);
+            rdst[1] = make_float4(rv1.x - cb1.x, rv1.y - cb1.y, rv1.z - cb1.z, rv1.w - cb1.w);
+          }
+          __syncwarp();
+#pragma unroll 1
+          for (int hh = 0; hh < 2; ++hh)
+            if ((rare >> (16 * hh)) & 1u) resolve_row_fullwarp(__shfl_sync(0xffffffffu, ent, 16 * hh));
         }
       }
       if (threadIdx.x == 0) NS2_RVQ_STAMP(5);
