@@ -97,6 +97,7 @@ typedef struct ns2_gemm_args {
 } ns2_gemm_args;
 
 #define NS2_GEMM_FLAG_SKIP_EPILOGUE 1  /* measurement aid: run the TMA/MMA mainloop only, write nothing (CTA-pair kernel) */
+#define NS2_GEMM_FLAG_WAVENET_ONE_PASS 2 /* tuning / A-B tests: WAVENET with two 256-column accumulators and a single epilogue pass */
 
 int ns2_gemm(const ns2_gemm_args* args, ns2_stream_t stream);
 

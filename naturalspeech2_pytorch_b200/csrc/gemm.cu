@@ -399,7 +399,7 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmDev& p, const TileCo
 // of this warp's 32 rows; hsel: column half.  Returns after the last TMEM read of the tile (stores may be in flight).
 template <int BN, int NACC, int EPI>
 __device__ __forceinline__ void epilogue_tile_tma8(const GemmDev& p, const TileCoord& t, uint32_t taddr, int row0,
-                                                   int hsel, Stager& st) {
+                                                   int hsel, Stager& st, int bias_off = 0) {
   const int tile_col0 = t.n_tile * BN;
   constexpr bool kTwo = (EPI == NS2_EPI_GEGLU || EPI == NS2_EPI_WAVENET);   // two accumulator regions per step
   constexpr int HALF = (EPI == NS2_EPI_GEGLU) ? 64 : BN / 2;                // output columns of this warp per tile
@@ -431,7 +431,7 @@ __device__ __forceinline__ void epilogue_tile_tma8(const GemmDev& p, const TileC
       if constexpr (EPI == NS2_EPI_BF16 || EPI == NS2_EPI_F32) {
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(ra[buf][i]);
-        if (p.bias != nullptr) add_vec<32>(v, p.bias + t.g * p.b_grs + tile_col0 + c);
+        if (p.bias != nullptr) add_vec<32>(v, p.bias + bias_off + t.g * p.b_grs + tile_col0 + c);
       } else if constexpr (EPI == NS2_EPI_GEGLU) {
         const float4* bv4 = reinterpret_cast<const float4*>(p.bias + t.g * p.b_grs + tile_col0 + c);
         const float4* bg4 = bv4 + 32;   // gate bias: + 128 columns
@@ -833,6 +833,260 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Gemm2Cfg<BN, NACC>::
 }
 
 // ------------------------------------------------------------------------------------------------
+// Wavenet residual block on CTA pairs, TWO-PASS accumulator (gemm2w_kernel).
+// y = tanh(z) sigmoid(z) + res(x),  z = (conv3(x) + b0) * gamma + beta   (ns2.py:619-636)
+// gemm2_kernel keeps conv3(x) and res(x) in two 256-column accumulators, i.e. all 512 TMEM columns: the epilogue
+// and the next tile's MMAs take turns (1.9 ms vs 1.45 ms mainloop-only per step).  Here one 256-column accumulator
+// serves both: phase 1 accumulates conv3(x); epilogue pass 1 replaces it IN TENSOR MEMORY by the gate value
+// (tcgen05.ld -> gate -> tcgen05.st); phase 2 accumulates res(x) on top; pass 2 adds the residual bias and stores
+// bf16.  Two accumulator stages fit, and tiles go through the pipeline in pairs (a, b):
+//     MMA:       P1(a)  P1(b)            P2(a)        P2(b)         P1(a') ...
+//     epilogue:         pass1(a)  pass1(b)     pass2(a)      pass2(b)
+// so every epilogue pass runs under MMAs of the other stage.
+// ------------------------------------------------------------------------------------------------
+template <int DUMMY>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Gemm2Cfg<256, 1>::THREADS, 1)
+    gemm2w_kernel(const __grid_constant__ GemmDev p) {
+  using Cfg = Gemm2Cfg<256, 1>;
+  constexpr int BN = 256;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
+  uint64_t* full_bar = bars;                           // [STAGES]  leader only
+  uint64_t* empty_bar = bars + Cfg::STAGES;            // [STAGES]  one per CTA, multicast commit
+  uint64_t* tfull1_bar = bars + 2 * Cfg::STAGES;       // [2] phase 1 complete (per CTA, multicast commit)
+  uint64_t* tfull2_bar = tfull1_bar + 2;               // [2] phase 2 complete
+  uint64_t* gready_bar = tfull2_bar + 2;               // [2] leader only: gate values are in TMEM (16 arrivals)
+  uint64_t* tempty_bar = gready_bar + 2;               // [2] leader only: accumulator stage drained (16 arrivals)
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int pair = blockIdx.x >> 1;
+  const int num_pairs = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmA);
+    tma_prefetch_desc(&p.tmB);
+    tma_prefetch_desc(&p.tmOut);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < Cfg::STAGES; ++i) {
+      mbar_init(smem_u32(&full_bar[i]), 1);
+      mbar_init(smem_u32(&empty_bar[i]), 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(&tfull1_bar[i]), 1);
+      mbar_init(smem_u32(&tfull2_bar[i]), 1);
+      mbar_init(smem_u32(&gready_bar[i]), 2 * Cfg::EPI_WARPS);
+      mbar_init(smem_u32(&tempty_bar[i]), 2 * Cfg::EPI_WARPS);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc_2cta(smem_u32(tmem_holder), 512);
+  tc_fence_before();
+  __syncwarp();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
+    if (warp == 0) {
+      // =============================== TMA producer (both CTAs; converged) ===================
+      uint32_t it = 0;
+      auto load_phase = [&](int tile, int want_acc) {
+        const TileCoord t = decode_tile<2 * BM>(p, tile);
+        const int dil = p.dil[t.g];
+        const int bn_eff = (p.n - t.n_tile * BN) < BN ? (p.n - t.n_tile * BN) : BN;
+        const int b_r0 = t.g * p.b_grs + t.n_tile * BN + static_cast<int>(rank) * (bn_eff / 2);
+        for (int s = 0; s < p.num_segs; ++s) {
+          const ns2_gemm_seg sg = p.segs[s];
+          if (sg.acc != want_acc) continue;
+          const int row0 = t.n0 + static_cast<int>(rank) * BM - sg.shift_units * dil;
+          const int a_c0 = t.g * p.a_gcs + sg.a_col_off;
+          const int kblocks = (sg.k_len + BK - 1) / BK;
+          for (int kb = 0; kb < kblocks; ++kb, ++it) {
+            const uint32_t stage = it % Cfg::STAGES;
+            const uint32_t phase = (it / Cfg::STAGES) & 1;
+            mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+            if (elect_one()) {
+              const uint32_t fb_leader = mapa_shared(smem_u32(&full_bar[stage]), 0);
+              if (leader) mbar_arrive_expect_tx(smem_u32(&full_bar[stage]), 2 * Cfg::STAGE_BYTES);
+              uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+              tma_load_3d_2sm(smem_u32(sa), &p.tmA, fb_leader, a_c0 + kb * BK, row0, t.b);
+              tma_load_2d_2sm(smem_u32(sa + Cfg::A_BYTES), &p.tmB, fb_leader, sg.b_col_off + kb * BK, b_r0);
+            }
+            __syncwarp();
+          }
+        }
+      };
+      for (int t0 = pair; t0 < p.num_tiles; t0 += 2 * num_pairs) {
+        const int t1 = t0 + num_pairs;
+        const bool has1 = t1 < p.num_tiles;
+        load_phase(t0, 0);
+        if (has1) load_phase(t1, 0);
+        load_phase(t0, 1);
+        if (has1) load_phase(t1, 1);
+      }
+    } else if (warp == 1) {
+      // =============================== MMA issuer (leader CTA only; converged) ================
+      if (leader) {
+        uint32_t it = 0, grp = 0;
+        auto mma_phase = [&](int tile, int want_acc, uint32_t d_tmem) {
+          const int n_tile = tile % p.tiles_n;
+          const int bn_eff = (p.n - n_tile * BN) < BN ? (p.n - n_tile * BN) : BN;
+          const uint32_t idesc = umma_idesc_f16(2 * BM, bn_eff, /*bf16*/ 1, 0, 0);
+          uint32_t started = want_acc;   // phase 2 accumulates on top of the gate values from its first MMA on
+          for (int s = 0; s < p.num_segs; ++s) {
+            if (p.segs[s].acc != want_acc) continue;
+            const int kblocks = (p.segs[s].k_len + BK - 1) / BK;
+            for (int kb = 0; kb < kblocks; ++kb, ++it) {
+              const uint32_t stage = it % Cfg::STAGES;
+              const uint32_t phase = (it / Cfg::STAGES) & 1;
+              mbar_wait(smem_u32(&full_bar[stage]), phase);
+              tc_fence_after();
+              const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+              const uint64_t da = umma_desc_sw128(sa, 16, 1024);
+              const uint64_t db = umma_desc_sw128(sa + Cfg::A_BYTES, 16, 1024);
+              if (elect_one()) {
+#pragma unroll
+                for (int k = 0; k < BK / 16; ++k)
+                  tc_mma_f16_2cta(d_tmem, da + 2 * k, db + 2 * k, idesc, started | (k > 0));
+                tc_commit_2cta(smem_u32(&empty_bar[stage]), 0b11);
+              }
+              __syncwarp();
+              started = 1;
+            }
+          }
+        };
+        for (int t0 = pair; t0 < p.num_tiles; t0 += 2 * num_pairs, ++grp) {
+          const int t1 = t0 + num_pairs;
+          const bool has1 = t1 < p.num_tiles;
+          const uint32_t ph = grp & 1;
+          mbar_wait(smem_u32(&tempty_bar[0]), ph ^ 1);
+          tc_fence_after();
+          mma_phase(t0, 0, tmem_base);
+          if (elect_one()) tc_commit_2cta(smem_u32(&tfull1_bar[0]), 0b11);
+          __syncwarp();
+          if (has1) {
+            mbar_wait(smem_u32(&tempty_bar[1]), ph ^ 1);
+            tc_fence_after();
+            mma_phase(t1, 0, tmem_base + 256);
+            if (elect_one()) tc_commit_2cta(smem_u32(&tfull1_bar[1]), 0b11);
+            __syncwarp();
+          }
+          mbar_wait(smem_u32(&gready_bar[0]), ph);
+          tc_fence_after();
+          mma_phase(t0, 1, tmem_base);
+          if (elect_one()) tc_commit_2cta(smem_u32(&tfull2_bar[0]), 0b11);
+          __syncwarp();
+          if (has1) {
+            mbar_wait(smem_u32(&gready_bar[1]), ph);
+            tc_fence_after();
+            mma_phase(t1, 1, tmem_base + 256);
+            if (elect_one()) tc_commit_2cta(smem_u32(&tfull2_bar[1]), 0b11);
+            __syncwarp();
+          }
+        }
+      }
+    }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
+    // =============================== epilogue (both CTAs, 8 warps each) =======================
+    const int ew = warp - 4;
+    const int quarter = ew & 3;
+    const int hsel = ew >> 2;
+    Stager st;
+    st.base = smem_u32(smem + Cfg::OFF_STG + ew * 2 * STG_BYTES);
+    st.count = 0;
+    st.lane = lane;
+    const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+    // pass 1: accumulator -> gate value, in place.  This warp owns columns [128 hsel, 128 hsel + 128) of its 32 rows.
+    auto pass1 = [&](int tile, uint32_t taddr) {
+      const TileCoord t = decode_tile<2 * BM>(p, tile);
+      const int tile_col0 = t.n_tile * BN;
+      uint32_t ra[2][32];
+      tmem_ld32(taddr + hsel * 128, ra[0]);
+#pragma unroll
+      for (int s = 0; s < 4; ++s) {
+        const int buf = s & 1;
+        const int c = hsel * 128 + s * 32;
+        tmem_ld_wait();
+        if (s + 1 < 4) tmem_ld32(taddr + c + 32, ra[buf ^ 1]);
+        if (tile_col0 + c < p.n) {   // a partial last n-tile is narrower (n is a multiple of 32)
+          const int col0 = tile_col0 + c;
+          const float4* b04 = reinterpret_cast<const float4*>(p.bias + t.g * p.b_grs + col0);
+          const float4* ga4 = reinterpret_cast<const float4*>(p.film + t.b * p.film_bs + t.g * p.film_gs + col0);
+          const float4* be4 = reinterpret_cast<const float4*>(p.film + t.b * p.film_bs + t.g * p.film_gs + col0 + p.n);
+          uint32_t gv[32];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float4 b0 = __ldg(b04 + q), g4 = __ldg(ga4 + q), e4 = __ldg(be4 + q);
+            const float b0a[4] = {b0.x, b0.y, b0.z, b0.w};
+            const float gaa[4] = {g4.x, g4.y, g4.z, g4.w}, bea[4] = {e4.x, e4.y, e4.z, e4.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int i = 4 * q + j;
+              const float z = fmaf(__uint_as_float(ra[buf][i]) + b0a[j], gaa[j], bea[j]);
+              // tanh(z) * sigmoid(z) with ONE MUFU: u = tanh(z/2); sigmoid = (1 + u)/2; tanh(z) = 2u / (1 + u^2), the
+              // reciprocal of w = 1 + u^2 in [1, 2] by a linear seed + two Newton steps (rel. err < 2e-5)
+              const float u = tanh_fast(0.5f * z);
+              const float w = fmaf(u, u, 1.0f);
+              float r = fmaf(-0.47058824f, w, 1.4117647f);
+              r = r * fmaf(-w, r, 2.0f);
+              r = r * fmaf(-w, r, 2.0f);
+              gv[i] = __float_as_uint((u * r) * (1.0f + u));
+            }
+          }
+          tmem_st32(taddr + c, gv);
+        }
+      }
+      tmem_st_wait();
+    };
+    uint32_t grp = 0;
+    for (int t0 = pair; t0 < p.num_tiles; t0 += 2 * num_pairs, ++grp) {
+      const int t1 = t0 + num_pairs;
+      const bool has1 = t1 < p.num_tiles;
+      const uint32_t ph = grp & 1;
+      for (int x = 0; x < (has1 ? 2 : 1); ++x) {
+        mbar_wait(smem_u32(&tfull1_bar[x]), ph);
+        tc_fence_after();
+        if (!p.skip_epilogue) pass1(x ? t1 : t0, lane_base + x * 256);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(&gready_bar[x]), 0));
+      }
+      for (int x = 0; x < (has1 ? 2 : 1); ++x) {
+        const TileCoord t = decode_tile<2 * BM>(p, x ? t1 : t0);
+        mbar_wait(smem_u32(&tfull2_bar[x]), ph);
+        tc_fence_after();
+        // pass 2: gate + res(x) is in the accumulator: + residual bias -> bf16 -> TMA store
+        if (!p.skip_epilogue)
+          epilogue_tile_tma8<BN, 1, NS2_EPI_BF16>(p, t, lane_base + x * 256,
+                                                  t.n0 + static_cast<int>(rank) * BM + quarter * 32, hsel, st, p.bias1_off);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(&tempty_bar[x]), 0));
+      }
+    }
+    if (elect_one()) tma_store_wait_all();
+    __syncwarp();
+  }
+
+  tc_fence_before();
+  __syncwarp();
+  cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_2cta(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
 template <int BN, int NACC, int EPI>
@@ -851,6 +1105,18 @@ template <int BN, int NACC, int EPI>
 static int launch_gemm2(const GemmDev& dev, cudaStream_t stream) {
   using Cfg = Gemm2Cfg<BN, NACC>;
   auto kern = gemm2_kernel<BN, NACC, EPI>;
+  NS2_CUDA_CHECK(set_max_smem_once(kern, Cfg::SMEM_BYTES));
+  int pairs = num_sms() / 2;
+  if (dev.num_tiles < pairs) pairs = dev.num_tiles;
+  kern<<<2 * pairs, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(dev);  // __cluster_dims__(2,1,1)
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  NS2_CUDA_CHECK(cudaGetLastError());
+  return kOk;
+}
+
+static int launch_gemm2w(const GemmDev& dev, cudaStream_t stream) {
+  using Cfg = Gemm2Cfg<256, 1>;
+  auto kern = gemm2w_kernel<0>;
   NS2_CUDA_CHECK(set_max_smem_once(kern, Cfg::SMEM_BYTES));
   int pairs = num_sms() / 2;
   if (dev.num_tiles < pairs) pairs = dev.num_tiles;
@@ -985,6 +1251,9 @@ extern "C" int ns2_gemm(const ns2_gemm_args* a, ns2_stream_t stream_) {
       case NS2_EPI_GEGLU:
         return launch_gemm2<256, 1, NS2_EPI_GEGLU>(dev, stream);
       case NS2_EPI_WAVENET:
+        // 256-wide tiles: the two-pass single-accumulator kernel (epilogue fully under the MMAs) unless the caller
+        // asks for the two-accumulator tile (A/B measurements)
+        if (bn == 256 && !(a->flags & NS2_GEMM_FLAG_WAVENET_ONE_PASS)) return launch_gemm2w(dev, stream);
         return bn == 256 ? launch_gemm2<256, 2, NS2_EPI_WAVENET>(dev, stream)
                          : launch_gemm2<128, 2, NS2_EPI_WAVENET>(dev, stream);
       default:

@@ -220,7 +220,10 @@ def run_gemm_fused():
         ok &= _report(f"geglu D{D} Di{Di}", out[..., :Di], ref, 3e-2, 1e-2)
         ok &= _report(f"geglu D{D} Di{Di} (pad cols zero)", out[..., Di:], torch.zeros_like(out[..., Di:]), 0, 0)
     # ---- wavenet block, 8 dilation groups in one launch ----
-    for (B, N, D, G) in [(2, 512, 512, 8), (2, 256, 128, 8), (3, 200, 512, 3)]:
+    # flags 0: two-pass single-accumulator kernel for 256-wide tiles (gemm2w_kernel); flags 2: the two-accumulator tile.
+    # (9, 1024, 512, 8): 576 tiles = 7-8 per CTA pair: several pipeline groups, odd and even tile counts
+    for (B, N, D, G, flags) in [(2, 512, 512, 8, 0), (2, 512, 512, 8, 2), (2, 256, 128, 8, 0), (3, 200, 512, 3, 0),
+                                (3, 200, 512, 3, 2), (9, 1024, 512, 8, 0)]:
         dils = [2 ** i for i in range(G)]
         x = (torch.randn(B, N, G * D, device=dev) * 0.5).bfloat16()  # group g reads columns [g*D, (g+1)*D)
         wc = (torch.randn(G, D, D, 3, device=dev) / math.sqrt(3 * D)).bfloat16()
@@ -233,7 +236,7 @@ def run_gemm_fused():
         segs = ops.conv3_segs(D) + [(0, 3 * D, D, 0, 1)]
         ops.gemm(x, wp, out, n=D, epilogue=ops.EPI_WAVENET, bias=bias, bias1_off=G * D, segs=segs,
                  film=film, film_group_stride=2 * D, groups=G, a_group_col_stride=D,
-                 b_group_row_stride=D, out_group_col_stride=D, dil=dils)
+                 b_group_row_stride=D, out_group_col_stride=D, dil=dils, flags=flags)
         refs = []
         for g in range(G):
             xg = x[:, :, g * D:(g + 1) * D]
@@ -243,7 +246,7 @@ def run_gemm_fused():
             y = y * gm + bt
             y = y.tanh() * y.sigmoid()
             refs.append(y + xg.float() @ wr[g].float().T + br[g])
-        ok &= _report(f"wavenet block B{B} N{N} D{D} G{G}", out, torch.cat(refs, dim=-1), 3e-2, 1e-2)
+        ok &= _report(f"wavenet block B{B} N{N} D{D} G{G} flags{flags}", out, torch.cat(refs, dim=-1), 3e-2, 1e-2)
     return ok
 
 
