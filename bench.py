@@ -342,6 +342,58 @@ def secondary_cfg3(dev, peaks):
             "step_frac_of_sustained_peak": round(tf / sus, 4)}
 
 
+def secondary_aligner(dev, peaks):
+    """`maximum_path` (aligner.py:88-122) at configs[4] scale — 32 samples x 100 phonemes x 1024 mel frames.
+    GPU time of the two kernels, the reference's own function on the host cores beside it, bit-exact check."""
+    import numpy as np
+    import torch
+    from naturalspeech2_pytorch_b200 import ops
+    b, t_x, t_y = 32, 100, 1024
+    g = torch.Generator().manual_seed(77)
+    value = torch.randn(b, t_y, t_x, generator=g).mul(2).softmax(-1).transpose(1, 2).contiguous()
+    x_lens = torch.randint(20, t_x + 1, (b,), generator=g)
+    y_lens = torch.randint(4 * t_x, t_y + 1, (b,), generator=g)
+    mask = ((torch.arange(t_x)[None, :, None] < x_lens[:, None, None])
+            & (torch.arange(t_y)[None, None, :] < y_lens[:, None, None])).float()
+    vd, md = value.to(dev), mask.to(dev)
+    for _ in range(3):
+        idx, path = ops.maximum_path(vd, md)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    iters = 20
+    e0.record()
+    for _ in range(iters):
+        idx, path = ops.maximum_path(vd, md)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    out = {"metric": "alignments/sec", "unit": "alignments/s", "value": round(b / (ms * 1e-3), 1),
+           "ms_per_call": round(ms, 4),
+           "workload": "maximum_path (monotonic alignment search), value/mask (32, 100, 1024) fp32, dense path out",
+           "roofline": {"bound": "latency (serial recursion over the 1024 frames, one CTA per sample); HBM for the "
+                                 "expansion kernel",
+                        "algorithmic_bytes": 3 * b * t_x * t_y * 4,
+                        "achieved_GBps": round(3 * b * t_x * t_y * 4 / (ms * 1e-3) / 1e9, 1),
+                        "peak_GBps": float(peaks.get("hbm_gbs", 6650.0))}}
+    try:
+        if import_reference() is None:
+            raise RuntimeError("baseline/_ref is not present")
+        import time
+        from naturalspeech2_pytorch.aligner import maximum_path as ref_mas
+        torch.set_num_threads(_host_threads())
+        t0 = time.perf_counter()
+        ref = ref_mas(value, mask)
+        cpu_s = time.perf_counter() - t0
+        out["bit_exact_vs_reference"] = bool(torch.equal(ref, path.cpu()))
+        out["cpu_reference"] = {"value": round(b / cpu_s, 1), "unit": "alignments/s", "cores": _host_threads(),
+                                "kind": "reference", "sample": f"the same 32 alignments, one call, {cpu_s:.3f} s"}
+    except Exception as e:
+        from oracle import aligner_oracle
+        ref = aligner_oracle.maximum_path(value[:4].numpy(), mask[:4].numpy())
+        out["bit_exact_vs_oracle_4_samples"] = bool(np.array_equal(ref, path[:4].cpu().numpy()))
+        out["cpu_reference"] = {"error": f"{type(e).__name__}: {e}"}
+    return out
+
+
 def train_step_dp(dev, world, peaks, steps=4, warmup=2):
     """configs[4]: conditioned diffusion TRAINING step (Model(512, depth 12, dim_prompt 512, condition_on_prompt) inside
     NaturalSpeech2.forward -> loss.backward() -> fused AdamW), 32 samples per GPU, data parallel: gradient all-reduce
@@ -609,7 +661,7 @@ def run_ours(args):
         if world == 1 and not args.no_secondary:
             del model
             torch.cuda.empty_cache()
-            for name, fn in (("rvq", secondary_rvq), ("cfg3", secondary_cfg3)):
+            for name, fn in (("rvq", secondary_rvq), ("cfg3", secondary_cfg3), ("aligner_mas", secondary_aligner)):
                 try:
                     secondary[name] = fn(dev, peaks)
                 except Exception as e:  # a secondary number must never take the headline line down

@@ -322,6 +322,20 @@ int ns2_film_wgrad(const float* dfilm, const float* t, int32_t batch, int64_t ro
 /*    ns2_accum_bf16       : acc (f32) += t (bf16); acc_bf16 (optional) = bf16(acc)   (joins a branch gradient) */
 int ns2_accum_bf16(float* acc, const void* t_bf16, int64_t count, void* acc_bf16, ns2_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * 9. Monotonic alignment search: `maximum_path(value, mask)` of naturalspeech2_pytorch/aligner.py:88-122 (called from
+ *    Aligner.forward aligner.py:214, reached from NaturalSpeech2.forward ns2.py:1578 in conditional training).
+ *    value, mask: f32 (batch, t_x, t_y) contiguous (t_x text positions <= 1024, t_y mel frames); mask holds 0/1.
+ *    Viterbi recursion over the frames with the reference's exact fp32 operations and tie rule, then the backtrack:
+ *      idx[b, j]     (int32, batch x t_y)  = text position aligned to frame j
+ *      path[b, i, j] (f32, optional)       = (idx[b, j] == i) * mask[b, i, j]      — bit-identical to the reference
+ *    neg_const = the reference's `const` (default -inf).  workspace: ns2_maximum_path_workspace_bytes() bytes of
+ *    scratch (1-bit decisions, batch x t_y x 128 B).
+ * ------------------------------------------------------------------------------------------------ */
+int64_t ns2_maximum_path_workspace_bytes(int32_t batch, int32_t t_x, int32_t t_y);
+int ns2_maximum_path(const float* value, const float* mask, int32_t batch, int32_t t_x, int32_t t_y, float neg_const,
+                     void* workspace, int64_t workspace_bytes, int32_t* idx, float* path, ns2_stream_t stream);
+
 /* Number of kernel launches issued through this library since load (for bench.py's gpu_launches). */
 int64_t ns2_launch_count(void);
 

@@ -9,5 +9,6 @@ from .model import Model  # noqa: F401
 from .diffusion import NaturalSpeech2  # noqa: F401
 from .codec import EncodecRVQ  # noqa: F401
 from . import parallel  # noqa: F401
+from .aligner import maximum_path  # noqa: F401
 
 __version__ = "0.1.0"

@@ -115,6 +115,8 @@ SIGNATURES = {
     "ns2_rvq_prepare": (C.c_int, [_P, _I32, _I32, _I32, _P, _P, _P, _P]),
     "ns2_rvq_encode": (C.c_int, [_P, _I64, _I32, _P, _P, _P, _P, _I32, _I32, _P, _P, _P]),
     "ns2_rvq_decode": (C.c_int, [_P, _I64, _I32, _I32, _I32, _P, _P, _P]),
+    "ns2_maximum_path_workspace_bytes": (C.c_int64, [_I32, _I32, _I32]),
+    "ns2_maximum_path": (C.c_int, [_P, _P, _I32, _I32, _I32, _F, _P, _I64, _P, _P, _P]),
     "ns2_rvq_ce": (C.c_int, [_P, _I64, _I32, _P, _P, _I32, _I32, _P, _P, _P, _P, _P]),
 }
 

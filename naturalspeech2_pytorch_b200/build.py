@@ -20,7 +20,7 @@ LIB_DIR = PKG_DIR / "lib"
 LIB_PATH = LIB_DIR / "libns2b200.so"
 OBJ_DIR = PKG_DIR / "build" / "obj"
 
-SOURCES = ["host_common.cu", "elementwise.cu", "gemm.cu", "attn.cu", "rvq.cu", "rvq_ce.cu", "wgrad.cu", "backward.cu", "attn_bwd.cu"]
+SOURCES = ["host_common.cu", "elementwise.cu", "gemm.cu", "attn.cu", "rvq.cu", "rvq_ce.cu", "wgrad.cu", "backward.cu", "attn_bwd.cu", "align.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

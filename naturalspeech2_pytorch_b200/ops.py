@@ -625,3 +625,26 @@ def accum_bf16(acc, t, acc_bf=None):
         _req(acc_bf, torch.bfloat16, "acc_bf")
     check(lib.ns2_accum_bf16(acc.data_ptr(), t.data_ptr(), acc.numel(), _ptr(acc_bf), _stream(acc)), "ns2_accum_bf16")
     return acc
+
+
+# --------------------------------------------------------------------------------------------------
+# Monotonic alignment search (aligner.py:88-122)
+# --------------------------------------------------------------------------------------------------
+def maximum_path(value: torch.Tensor, mask: torch.Tensor, neg_const: float = float("-inf"), *,
+                 want_path: bool = True) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    """(idx (b, t_y) int32, path (b, t_x, t_y) f32 or None) for value/mask (b, t_x, t_y) f32 contiguous."""
+    lib = _lib.load()
+    _req(value, torch.float32, "value")
+    _req(mask, torch.float32, "mask")
+    if value.dim() != 3 or value.shape != mask.shape:
+        raise ValueError(f"value and mask must both be (b, t_x, t_y); got {tuple(value.shape)} / {tuple(mask.shape)}")
+    if not (value.is_contiguous() and mask.is_contiguous()):
+        raise ValueError("value and mask must be contiguous")
+    b, t_x, t_y = value.shape
+    idx = torch.empty((b, t_y), dtype=torch.int32, device=value.device)
+    path = torch.empty_like(value) if want_path else None
+    ws_bytes = int(lib.ns2_maximum_path_workspace_bytes(b, t_x, t_y))
+    ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=value.device)
+    check(lib.ns2_maximum_path(value.data_ptr(), mask.data_ptr(), b, t_x, t_y, float(neg_const), ws.data_ptr(),
+                               ws_bytes, idx.data_ptr(), _ptr(path), _stream(value)), "ns2_maximum_path")
+    return idx, path

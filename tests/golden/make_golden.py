@@ -262,6 +262,46 @@ def rvq_goldens():
     print("rvq:", {k: v.shape for k, v in out.items()})
 
 
+def aligner_cases():
+    """Seeded inputs of the monotonic-alignment fixtures: name -> (value (b,t_x,t_y) f32, x_lens, y_lens)."""
+    cases = {}
+    g = torch.Generator().manual_seed(4321)
+    # soft alignments as Aligner.forward produces them (softmax over the text axis), ragged lengths
+    v = torch.randn(3, 90, 37, generator=g).mul(3).softmax(dim=-1).transpose(1, 2).contiguous()
+    cases["soft_ragged"] = (v, [37, 20, 5], [90, 64, 33])
+    # more text positions than frames, signed scores
+    cases["tall_signed"] = (torch.randn(2, 130, 50, generator=g), [130, 77], [50, 41])
+    # heavy ties: scores quantised to quarters
+    cases["ties"] = (torch.randint(0, 4, (2, 70, 45), generator=g).float() / 4, [70, 33], [45, 45])
+    cases["wide16"] = (torch.rand(1, 300, 40, generator=g), [300], [40])
+    cases["wide32"] = (torch.rand(1, 600, 24, generator=g), [590], [23])
+    cases["narrow"] = (torch.rand(2, 9, 130, generator=g), [9, 1], [130, 2])
+    return cases
+
+
+def aligner_masks(v, x_lens, y_lens):
+    b, t_x, t_y = v.shape
+    xm = (torch.arange(t_x)[None, :] < torch.tensor(x_lens)[:, None]).float()
+    ym = (torch.arange(t_y)[None, :] < torch.tensor(y_lens)[:, None]).float()
+    return xm[:, :, None] * ym[:, None, :]                      # attn_mask of Aligner.forward, aligner.py:208-211
+
+
+def aligner_goldens():
+    """maximum_path of the reference (aligner.py:88-122) on the seeded cases -> aligner_mas.npz."""
+    from naturalspeech2_pytorch.aligner import maximum_path
+    out = {}
+    for name, (v, xl, yl) in aligner_cases().items():
+        mask = aligner_masks(v, xl, yl)
+        path = maximum_path(v, mask)
+        assert path.dtype == torch.float32 and set(path.unique().tolist()) <= {0.0, 1.0}
+        out[f"{name}_value"] = v.numpy()
+        out[f"{name}_xlens"] = np.asarray(xl, dtype=np.int64)
+        out[f"{name}_ylens"] = np.asarray(yl, dtype=np.int64)
+        out[f"{name}_path"] = path.numpy().astype(np.uint8)
+    np.savez_compressed(HERE / "aligner_mas.npz", **out)
+    print("aligner:", {k: v.shape for k, v in out.items() if k.endswith("_path")})
+
+
 def math_log2(v):
     import math
     return math.log2(v)
@@ -282,6 +322,8 @@ def main():
         diffusion_goldens(ns2)
     if not only or "grads" in only:
         gradient_goldens(ns2)
+    if not only or "aligner" in only:
+        aligner_goldens()
 
 
 if __name__ == "__main__":

@@ -65,3 +65,15 @@ def oracle_config(kwargs: dict):
 def err_stats(got: np.ndarray, ref: np.ndarray):
     d = np.abs(np.asarray(got, dtype=np.float64) - np.asarray(ref, dtype=np.float64))
     return float(d.max()), float(np.sqrt((d ** 2).mean()))
+
+
+def aligner_golden_cases():
+    """(name, value, mask, reference path) of tests/golden/aligner_mas.npz; masks are rebuilt from the stored lengths
+    exactly as Aligner.forward does (aligner.py:208-211)."""
+    z = np.load(GOLDEN / "aligner_mas.npz")
+    for name in sorted(k[:-6] for k in z.files if k.endswith("_value")):
+        value = z[f"{name}_value"]
+        b, t_x, t_y = value.shape
+        xm = (np.arange(t_x)[None, :] < z[f"{name}_xlens"][:, None]).astype(np.float32)
+        ym = (np.arange(t_y)[None, :] < z[f"{name}_ylens"][:, None]).astype(np.float32)
+        yield name, value, xm[:, :, None] * ym[:, None, :], z[f"{name}_path"]

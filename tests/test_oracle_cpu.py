@@ -157,3 +157,19 @@ def test_torch_port_matches_reference_at_benchmarked_dims(name):
     emax, _ = err_stats(golden_rows(z, out.numpy()), z["out_fp64"])
     ref32 = float(z["stats_out_fp32"][0])
     assert emax < 5 * ref32 + 1e-6, (emax, ref32)
+
+
+def test_aligner_oracle_matches_reference_goldens():
+    """oracle.aligner_oracle.maximum_path == the reference's maximum_path (aligner.py:88-122) on every fixture,
+    bit for bit (0/1 path)."""
+    from helpers import aligner_golden_cases
+    from oracle import aligner_oracle
+    n = 0
+    for name, value, mask, ref_path in aligner_golden_cases():
+        path, idx = aligner_oracle.maximum_path(value, mask, return_index=True)
+        np.testing.assert_array_equal(path, ref_path.astype(np.float32), err_msg=name)
+        b, t_x, t_y = value.shape
+        onehot = (np.arange(t_x)[None, :, None] == idx[:, None, :]).astype(np.float32) * mask
+        np.testing.assert_array_equal(onehot, path, err_msg=name)
+        n += 1
+    assert n >= 6
