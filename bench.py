@@ -394,6 +394,65 @@ def secondary_aligner(dev, peaks):
     return out
 
 
+def secondary_prompt_encoder(dev, peaks):
+    """SpeechPromptEncoder (ns2.py:289-341, default dims: 8 k=9 convs up to 2048 channels + 6-layer
+    transformer) on the configs[2] prompt batch (16, 103, 128-d codec latents).  Once-per-sample work ahead of the
+    denoiser loop; the reference module on the host cores is timed beside it on 2 of the 16 prompts."""
+    import time
+    import torch
+    from naturalspeech2_pytorch_b200.encoders import SpeechPromptEncoder
+    B, Np, Dc = 16, 103, 128
+    torch.manual_seed(0)
+    enc = SpeechPromptEncoder(dim_codebook=Dc).to(dev).eval()
+    x_host = torch.randn(B, Np, Dc, generator=torch.Generator().manual_seed(5))
+    x = x_host.to(dev)
+    for _ in range(3):
+        y = enc(x)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    iters = 10
+    e0.record()
+    for _ in range(iters):
+        y = enc(x)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    dims = [Dc, 256, 2048, 2048, 2048, 2048, 512, 512, 512]
+    conv_flops = 2.0 * Np * 9 * sum(a * b for a, b in zip(dims[:-1], dims[1:]))
+    D, Di, depth = 512, 1365, 6
+    tr_flops = depth * (2.0 * Np * D * 3 * D + 4.0 * Np * Np * D + 2.0 * Np * D * D + 2.0 * Np * D * 2 * Di + 2.0 * Np * Di * D)
+    flops = B * (conv_flops + tr_flops)
+    burst = float(peaks.get("bf16_tflops", 1590.0))
+    out = {"metric": "prompts/sec", "unit": "prompts/s", "value": round(B / (ms * 1e-3), 1), "ms_per_batch": round(ms, 4),
+           "workload": "SpeechPromptEncoder(dim_codebook=128) default dims, prompt batch (16, 103, 128), forward only",
+           "isfinite": bool(torch.isfinite(y).all()),
+           "roofline": {"bound": "tensor", "achieved": round(flops / (ms * 1e-3) / 1e12, 1), "peak": burst,
+                        "unit": "TFLOP/s", "frac": round(flops / (ms * 1e-3) / 1e12 / burst, 4),
+                        "flops_per_prompt": conv_flops + tr_flops,
+                        "note": "103 of the 128 rows of every tile are real positions (one M tile per prompt)"}}
+    try:
+        ns2 = import_reference()
+        if ns2 is None:
+            raise RuntimeError("baseline/_ref is not present")
+        torch.set_num_threads(_host_threads())
+        ref = ns2.SpeechPromptEncoder(dim_codebook=Dc).eval()
+        ref.load_state_dict(enc.state_dict())
+        with torch.no_grad():
+            ref(x_host[:2])
+            t0 = time.perf_counter()
+            yr = ref(x_host[:2])
+            cpu_s = time.perf_counter() - t0
+        d = (y[:2].cpu() - yr).abs()
+        out["parity_vs_reference_fp32"] = {"max_abs": float(d.max()), "rms": float(d.pow(2).mean().sqrt()),
+                                            "out_std": float(yr.std())}
+        out["cpu_reference"] = {"value": round(2 / cpu_s, 2), "unit": "prompts/s", "cores": _host_threads(),
+                                "kind": "reference", "sample": f"2 of the 16 prompts, one call, {cpu_s:.3f} s"}
+    except Exception as e:
+        out["cpu_reference"] = {"error": f"{type(e).__name__}: {e}"}
+    del enc
+    torch.cuda.empty_cache()
+    return out
+
+
 def train_step_dp(dev, world, peaks, steps=4, warmup=2):
     """configs[4]: conditioned diffusion TRAINING step (Model(512, depth 12, dim_prompt 512, condition_on_prompt) inside
     NaturalSpeech2.forward -> loss.backward() -> fused AdamW), 32 samples per GPU, data parallel: gradient all-reduce
@@ -661,7 +720,8 @@ def run_ours(args):
         if world == 1 and not args.no_secondary:
             del model
             torch.cuda.empty_cache()
-            for name, fn in (("rvq", secondary_rvq), ("cfg3", secondary_cfg3), ("aligner_mas", secondary_aligner)):
+            for name, fn in (("rvq", secondary_rvq), ("cfg3", secondary_cfg3), ("aligner_mas", secondary_aligner),
+                             ("prompt_encoder", secondary_prompt_encoder)):
                 try:
                     secondary[name] = fn(dev, peaks)
                 except Exception as e:  # a secondary number must never take the headline line down

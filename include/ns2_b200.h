@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define NS2_ABI_VERSION 2
+#define NS2_ABI_VERSION 3
 
 typedef void* ns2_stream_t; /* cudaStream_t */
 
@@ -38,7 +38,8 @@ int ns2_abi_version(void);
  *                  * B[g*b_group_row_stride + j, segs[s].b_col_off + k]
  * where rows of A with a negative (or >= a_rows) position read as zero — this is the causal left padding
  * of CausalConv1d (ns2.py:583-595): a k=3 dilated causal conv is three segments with shift_units 2,1,0.
- * A Linear layer (nn.Linear: ns2.py:1021,1024,1051-1053,783) is one segment with shift 0.
+ * A Linear layer (nn.Linear: ns2.py:1021,1024,1051-1053,783) is one segment with shift 0.  A "same"-padded Conv1d
+ * (kernel 2p+1, padding p: SpeechPromptEncoder ns2.py:316-320) is 2p+1 segments with shift_units p, p-1, ..., -p.
  *
  * Epilogues (all accumulate in fp32):
  *   NS2_EPI_BF16     out_bf16 = acc0 + bias
@@ -54,7 +55,7 @@ int ns2_abi_version(void);
  * All k_len must be multiples of 64 unless the segment ends at the last column of A and B.
  * ------------------------------------------------------------------------------------------------ */
 enum { NS2_EPI_BF16 = 0, NS2_EPI_F32 = 1, NS2_EPI_GEGLU = 2, NS2_EPI_WAVENET = 3 };
-#define NS2_GEMM_MAX_SEGS 8
+#define NS2_GEMM_MAX_SEGS 12 /* a k=9 convolution (SpeechPromptEncoder, ns2.py:316-320) is 9 segments */
 #define NS2_GEMM_MAX_GROUPS 8
 
 typedef struct ns2_gemm_seg {
@@ -97,6 +98,8 @@ typedef struct ns2_gemm_args {
 } ns2_gemm_args;
 
 #define NS2_GEMM_FLAG_SKIP_EPILOGUE 1  /* measurement aid: run the TMA/MMA mainloop only, write nothing (CTA-pair kernel) */
+#define NS2_GEMM_FLAG_SILU 4 /* BF16 / F32 epilogues: out = silu(acc + bias) (+ resid) — Conv1d + nn.SiLU of the prompt
+                               encoder (ns2.py:316-320) and CausalConv1d + SiLU of the phoneme encoder (ns2.py:255-257) */
 #define NS2_GEMM_FLAG_WAVENET_ONE_PASS 2 /* tuning / A-B tests: WAVENET with two 256-column accumulators and a single epilogue pass */
 
 int ns2_gemm(const ns2_gemm_args* args, ns2_stream_t stream);
@@ -221,6 +224,10 @@ int ns2_select_rows(const uint8_t* drop_mask, const float* null_row, const float
                     ns2_stream_t stream);
 int ns2_transpose_cast(const float* x, int32_t batch, int32_t channels, int32_t length,
                        void* out_bf16, ns2_stream_t stream);
+/*    ns2_embedding_bf16   : out_bf16[r,:] = bf16(table[ids[r] < 0 ? pad_id : ids[r], :]) — nn.Embedding of the phoneme
+ *                           encoder with its padding substitution (ns2.py:253, 279-282); ids int64, table f32 */
+int ns2_embedding_bf16(const int64_t* ids, int64_t rows, const float* table, int32_t num_rows, int32_t dim,
+                       int32_t pad_id, void* out_bf16, ns2_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * 6. Diffusion element-wise steps, fp32 (NaturalSpeech2.forward ns2.py:1621-1666; ddim_sample 1392-1429).

@@ -11,12 +11,13 @@ from pathlib import Path
 _LIB_PATH = Path(__file__).resolve().parent / "lib" / "libns2b200.so"
 
 NS2_EPI_BF16, NS2_EPI_F32, NS2_EPI_GEGLU, NS2_EPI_WAVENET = 0, 1, 2, 3
-NS2_GEMM_MAX_SEGS = 8
+NS2_GEMM_MAX_SEGS = 12
 NS2_GEMM_MAX_GROUPS = 8
 NS2_MSE_SCRATCH_PER_SAMPLE = 64
 NS2_RVQ_STATS_LEN = 260
 NS2_OBJ_V, NS2_OBJ_EPS, NS2_OBJ_X0 = 0, 1, 2
-NS2_ABI_VERSION = 2
+NS2_GEMM_FLAG_SKIP_EPILOGUE, NS2_GEMM_FLAG_WAVENET_ONE_PASS, NS2_GEMM_FLAG_SILU = 1, 2, 4
+NS2_ABI_VERSION = 3
 
 
 class GemmSeg(C.Structure):
@@ -97,6 +98,7 @@ SIGNATURES = {
     "ns2_cast_bf16": (C.c_int, [_P, _P, _I64, _P, _P]),
     "ns2_mean_rows": (C.c_int, [_P, _I32, _I32, _I32, _P, _P]),
     "ns2_transpose_cast": (C.c_int, [_P, _I32, _I32, _I32, _P, _P]),
+    "ns2_embedding_bf16": (C.c_int, [_P, _I64, _P, _I32, _I32, _I32, _P, _P]),
     "ns2_cond_inject": (C.c_int, [_P, _P, _P, _P, _I32, _I32, _I32, _I32, _P, _P]),
     "ns2_select_rows": (C.c_int, [_P, _P, _P, _I64, _I32, _I32, _P, _I64, _I32, _P]),
     "ns2_q_sample": (C.c_int, [_P, _P, _P, _P, _I32, _I64, _P, _P, _I32, _P]),

@@ -368,6 +368,27 @@ __global__ void __launch_bounds__(256) cfg_combine_kernel(const float4* __restri
   }
 }
 
+// token embedding lookup -> bf16 rows (nn.Embedding of PhonemeEncoder, ns2.py:253, 279-282): negative ids are padding
+// and read row `pad_id`
+__global__ void __launch_bounds__(256) embedding_bf16_kernel(const long long* __restrict__ ids, long long rows,
+                                                             const float* __restrict__ table, int dim, int num_rows,
+                                                             int pad_id, __nv_bfloat16* __restrict__ out) {
+  const int per_row = dim / 4;
+  for (long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e < rows * per_row;
+       e += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = e / per_row;
+    const int c4 = static_cast<int>(e % per_row);
+    long long id = __ldg(ids + r);
+    if (id < 0) id = pad_id;
+    id = id < num_rows ? id : num_rows - 1;
+    const float4 v = __ldg(reinterpret_cast<const float4*>(table + id * dim) + c4);
+    uint2 w;
+    w.x = pack_bf16x2(v.x, v.y);
+    w.y = pack_bf16x2(v.z, v.w);
+    reinterpret_cast<uint2*>(out + r * dim)[c4] = w;
+  }
+}
+
 static cudaError_t configure_small_linear() { return set_max_smem_once(small_linear_kernel, 200 * 1024); }
 
 static unsigned grid_for(long long n4) {
@@ -383,6 +404,22 @@ using namespace ns2;
 extern "C" {
 
 int64_t ns2_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int ns2_embedding_bf16(const int64_t* ids, int64_t rows, const float* table, int32_t num_rows, int32_t dim,
+                       int32_t pad_id, void* out_bf16, ns2_stream_t stream) {
+  NS2_REQUIRE(rows >= 0 && num_rows > 0 && dim > 0 && dim % 4 == 0, "embedding_bf16: bad sizes");
+  NS2_REQUIRE(pad_id >= 0 && pad_id < num_rows, "embedding_bf16: pad_id %d outside the table", pad_id);
+  if (rows == 0) return kOk;
+  NS2_REQUIRE(ids && table && out_bf16, "embedding_bf16: null pointer");
+  NS2_REQUIRE((reinterpret_cast<uintptr_t>(table) & 15) == 0 && (reinterpret_cast<uintptr_t>(out_bf16) & 7) == 0,
+              "embedding_bf16: table must be 16-byte and out 8-byte aligned");
+  embedding_bf16_kernel<<<grid_for(rows * (dim / 4)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const long long*>(ids), rows, table, dim, num_rows, pad_id,
+      static_cast<__nv_bfloat16*>(out_bf16));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  NS2_CUDA_CHECK(cudaGetLastError());
+  return kOk;
+}
 
 int ns2_rmsnorm_film(const float* x, int64_t x_row_stride, int64_t rows, int32_t dim,
                      int32_t rows_per_batch, const float* gamma, const float* film,

@@ -51,6 +51,7 @@ struct GemmDev {
   const float* film;
   long long film_bs;
   int film_gs;
+  int act;            // BF16 / F32 epilogues: 0 = none, 1 = SiLU applied to acc + bias (ns2_gemm_args.flags & NS2_GEMM_FLAG_SILU)
   int skip_epilogue;  // measurement aid (ns2_gemm_args.flags & NS2_GEMM_FLAG_SKIP_EPILOGUE): mainloop-only timing
   long long* timeline;  // bring-up aid (ns2_gemm_args.debug_timeline): clock64 stamps of CTA pair 0, else NULL
 };
@@ -113,6 +114,13 @@ __device__ __forceinline__ void add_vec(float (&v)[W], const float* __restrict__
   }
 }
 
+// SiLU of conv / linear outputs (nn.SiLU after the SpeechPromptEncoder convs, ns2.py:316-320)
+template <int W>
+__device__ __forceinline__ void silu_vec(float (&v)[W]) {
+#pragma unroll
+  for (int i = 0; i < W; ++i) v[i] = __fdividef(v[i], 1.0f + __expf(-v[i]));
+}
+
 template <int W>
 __device__ __forceinline__ void store_bf16(const float (&v)[W], __nv_bfloat16* dst) {
   uint4* o4 = reinterpret_cast<uint4*>(dst);
@@ -143,6 +151,7 @@ __device__ __forceinline__ void epi_plain_chunk(const GemmDev& p, const TileCoor
   float v[W];
   tmem_load_f32<W>(taddr + tc, v);
   if (p.bias != nullptr) add_vec<W>(v, p.bias + t.g * p.b_grs + col0);
+  if (p.act != 0) silu_vec<W>(v);
   if (!row_ok) return;
   if constexpr (EPI == NS2_EPI_BF16) {
     store_bf16<W>(v, reinterpret_cast<__nv_bfloat16*>(p.out) + grow * p.out_rs + t.g * p.out_gcs + col0);
@@ -299,6 +308,7 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmDev& p, const TileCo
         float v[32];
         tmem_load_f32<32>(taddr + oc + h * 32, v);
         if (p.bias != nullptr) add_vec<32>(v, p.bias + t.g * p.b_grs + tile_col0 + oc + h * 32);
+        if (p.act != 0) silu_vec<32>(v);
         put_bf16x32(st, box, h, v);
       }
       st.submit(&p.tmOut, box, t.g * p.out_gcs + tile_col0 + oc, row0, t.b, false);
@@ -311,6 +321,7 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmDev& p, const TileCo
       float v[32];
       tmem_load_f32<32>(taddr + oc, v);
       if (p.bias != nullptr) add_vec<32>(v, p.bias + t.g * p.b_grs + tile_col0 + oc);
+      if (p.act != 0) silu_vec<32>(v);
 #pragma unroll
       for (int q = 0; q < 8; ++q)
         st.put(box, q, make_uint4(__float_as_uint(v[4 * q]), __float_as_uint(v[4 * q + 1]),
@@ -432,6 +443,7 @@ __device__ __forceinline__ void epilogue_tile_tma8(const GemmDev& p, const TileC
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(ra[buf][i]);
         if (p.bias != nullptr) add_vec<32>(v, p.bias + bias_off + t.g * p.b_grs + tile_col0 + c);
+        if (p.act != 0) silu_vec<32>(v);
       } else if constexpr (EPI == NS2_EPI_GEGLU) {
         const float4* bv4 = reinterpret_cast<const float4*>(p.bias + t.g * p.b_grs + tile_col0 + c);
         const float4* bg4 = bv4 + 32;   // gate bias: + 128 columns
@@ -1237,6 +1249,9 @@ extern "C" int ns2_gemm(const ns2_gemm_args* a, ns2_stream_t stream_) {
   dev.film = a->film;
   dev.film_bs = a->film_batch_stride;
   dev.film_gs = a->film_group_stride;
+  dev.act = (a->flags & NS2_GEMM_FLAG_SILU) ? 1 : 0;
+  NS2_REQUIRE(dev.act == 0 || a->epilogue == NS2_EPI_BF16 || a->epilogue == NS2_EPI_F32,
+              "ns2_gemm: NS2_GEMM_FLAG_SILU only applies to the BF16 / F32 epilogues");
   dev.skip_epilogue = (a->flags & NS2_GEMM_FLAG_SKIP_EPILOGUE) ? 1 : 0;
   dev.timeline = reinterpret_cast<long long*>(a->debug_timeline);
 

@@ -341,6 +341,21 @@ def transpose_cast(x: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
 OBJECTIVES = {"v": _lib.NS2_OBJ_V, "eps": _lib.NS2_OBJ_EPS, "x0": _lib.NS2_OBJ_X0}
 
 
+def embedding_bf16(ids: torch.Tensor, table: torch.Tensor, out: torch.Tensor, pad_id: int) -> torch.Tensor:
+    """out[..., :] = bf16(table[ids < 0 ? pad_id : ids]) — nn.Embedding + padding substitution (ns2.py:279-282)."""
+    lib = _lib.load()
+    _req(ids, torch.int64, "ids")
+    _req(table, torch.float32, "table")
+    _req(out, torch.bfloat16, "out")
+    if not (ids.is_contiguous() and table.is_contiguous() and out.is_contiguous()):
+        raise ValueError("embedding_bf16 needs contiguous tensors")
+    if out.numel() != ids.numel() * table.shape[1]:
+        raise ValueError("out must hold one table row per id")
+    check(lib.ns2_embedding_bf16(ids.data_ptr(), ids.numel(), table.data_ptr(), table.shape[0], table.shape[1],
+                                 int(pad_id), out.data_ptr(), _stream(out)), "ns2_embedding_bf16")
+    return out
+
+
 def q_sample(x0, noise, alpha, sigma, x_t, target=None, objective: str = "v"):
     """x_t = alpha x0 + sigma noise; target of the chosen parameterisation (ns2.py:1631-1644)."""
     lib = _lib.load()

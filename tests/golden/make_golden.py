@@ -262,6 +262,50 @@ def rvq_goldens():
     print("rvq:", {k: v.shape for k, v in out.items()})
 
 
+ENCODER_CASES = {
+    # name: (class name, ctor kwargs, input spec)
+    # the reference annotates dims as Tuple[int] (beartype: a 1-tuple), so small stacks have ONE conv; the default
+    # 8-conv stack (256, 2048 x4, 512 x3) is covered by spe_full (depth 1 to keep the fp64 run short)
+    "spe_small": ("SpeechPromptEncoder", dict(dim_codebook=128, dims=(256,), depth=2, heads=4), (2, 103)),
+    "spe_long": ("SpeechPromptEncoder", dict(dim_codebook=128, dims=(256,), depth=2, heads=4), (1, 300)),
+    "spe_full": ("SpeechPromptEncoder", dict(dim_codebook=128, depth=1), (1, 103)),
+    "phon_small": ("PhonemeEncoder", dict(num_tokens=50, dim=128, dim_hidden=128, depth=2, heads=2), (2, 37)),
+}
+
+
+def encoder_inputs(name, cls, kwargs, spec):
+    B, T = spec
+    if cls == "PhonemeEncoder":
+        ids = torch.randint(0, kwargs["num_tokens"], (B, T), generator=torch.Generator().manual_seed(21))
+        ids[1, T - 9:] = -1                                   # padding (ns2.py:279-280)
+        return ids
+    return seeded((B, T, kwargs["dim_codebook"]), 22)
+
+
+def encoder_goldens(ns2):
+    """SpeechPromptEncoder / PhonemeEncoder of the reference (ns2.py:228-341): fp64, fp32 and autocast-bf16 outputs."""
+    out = {}
+    for name, (cls, kwargs, spec) in ENCODER_CASES.items():
+        torch.manual_seed(0)
+        enc = getattr(ns2, cls)(**kwargs).eval()
+        fill_module(enc, seed=1234)
+        x = encoder_inputs(name, cls, kwargs, spec)
+        with torch.no_grad():
+            y32 = enc(x)
+            e64 = getattr(ns2, cls)(**kwargs).double().eval()
+            e64.load_state_dict({k: v.double() for k, v in enc.state_dict().items()})
+            y64 = e64(x if x.dtype == torch.int64 else x.double())
+            with torch.autocast("cpu", dtype=torch.bfloat16):
+                y16 = enc(x).float()
+        print(f"{name}: out_std={y64.std():.3f} |fp32-fp64|max={(y32.double() - y64).abs().max():.2e} "
+              f"|bf16autocast-fp64|max={(y16.double() - y64).abs().max():.2e}")
+        out[f"{name}_in"] = x.numpy()
+        out[f"{name}_fp64"] = y64.numpy()
+        out[f"{name}_bf16_autocast"] = y16.numpy()
+        out[f"{name}_keys"] = np.array(repr([(k, tuple(v.shape)) for k, v in enc.state_dict().items()]))
+    np.savez_compressed(HERE / "encoders.npz", **out)
+
+
 def aligner_cases():
     """Seeded inputs of the monotonic-alignment fixtures: name -> (value (b,t_x,t_y) f32, x_lens, y_lens)."""
     cases = {}
@@ -324,6 +368,8 @@ def main():
         gradient_goldens(ns2)
     if not only or "aligner" in only:
         aligner_goldens()
+    if not only or "encoders" in only:
+        encoder_goldens(ns2)
 
 
 if __name__ == "__main__":

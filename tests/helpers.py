@@ -77,3 +77,22 @@ def aligner_golden_cases():
         xm = (np.arange(t_x)[None, :] < z[f"{name}_xlens"][:, None]).astype(np.float32)
         ym = (np.arange(t_y)[None, :] < z[f"{name}_ylens"][:, None]).astype(np.float32)
         yield name, value, xm[:, :, None] * ym[:, None, :], z[f"{name}_path"]
+
+
+ENCODER_CASES = ["spe_small", "spe_long", "spe_full", "phon_small"]
+
+
+def encoder_case(name: str):
+    """(class name, ctor kwargs, input tensor, fp64 reference output, reference autocast-bf16 output, key list)."""
+    from golden.make_golden import ENCODER_CASES as SPEC
+    z = np.load(GOLDEN / "encoders.npz")
+    cls, kwargs, _ = SPEC[name]
+    keys = ast.literal_eval(str(z[f"{name}_keys"]))
+    return cls, dict(kwargs), torch.from_numpy(z[f"{name}_in"]), z[f"{name}_fp64"], z[f"{name}_bf16_autocast"], keys
+
+
+def build_encoder(cls: str, kwargs: dict, seed: int = 1234, device="cpu"):
+    from naturalspeech2_pytorch_b200 import encoders
+    m = getattr(encoders, cls)(**kwargs)
+    fill_module(m, seed)
+    return m.to(device).eval()

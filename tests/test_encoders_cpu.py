@@ -1,0 +1,39 @@
+"""CPU: conditioning-encoder oracle against the reference goldens; drop-in surface (state_dict keys / shapes)."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import ENCODER_CASES, build_encoder, encoder_case
+
+
+@pytest.mark.parametrize("name", ENCODER_CASES)
+def test_encoder_oracle_matches_reference_fp64(name):
+    from oracle import encoders_oracle
+    cls, kwargs, x, ref64, _, _ = encoder_case(name)
+    enc = build_encoder(cls, kwargs)
+    P = {k: v.double() for k, v in enc.state_dict().items()}
+    if cls == "PhonemeEncoder":
+        out = encoders_oracle.phoneme_encoder(P, x, heads=kwargs.get("heads", 8))
+    else:
+        out = encoders_oracle.speech_prompt_encoder(P, x.double(), heads=kwargs.get("heads", 8))
+    assert np.abs(out.numpy() - ref64).max() < 1e-9
+
+
+@pytest.mark.parametrize("name", ENCODER_CASES)
+def test_encoder_state_dict_matches_reference(name):
+    """Same keys, order and shapes as the reference module (recorded by make_golden.py from the reference itself)."""
+    cls, kwargs, _, _, _, keys = encoder_case(name)
+    enc = build_encoder(cls, kwargs)
+    assert [(k, tuple(v.shape)) for k, v in enc.state_dict().items()] == [(k, tuple(s)) for k, s in keys]
+
+
+def test_encoders_reject_cpu_inputs_and_masks():
+    cls, kwargs, x, *_ = encoder_case("phon_small")
+    enc = build_encoder(cls, kwargs)
+    with pytest.raises(ValueError):
+        enc(x)
+    with pytest.raises(NotImplementedError):
+        enc(x, mask=torch.ones_like(x, dtype=torch.bool))
+    cls, kwargs, x, *_ = encoder_case("spe_small")
+    with pytest.raises(ValueError):
+        build_encoder(cls, kwargs)(x)

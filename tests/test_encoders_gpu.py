@@ -1,0 +1,61 @@
+"""GPU: SpeechPromptEncoder / PhonemeEncoder through the C ABI against the reference's fp64 goldens.
+Tolerance protocol of the denoiser: our max-abs and rms error must not exceed the error of the
+reference's own autocast-bf16 run on the same inputs, plus an absolute bound at output std ~ 1."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import ENCODER_CASES, build_encoder, encoder_case, err_stats
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name", ENCODER_CASES)
+def test_encoder_matches_reference_golden(name):
+    cls, kwargs, x, ref64, ref_bf16, _ = encoder_case(name)
+    enc = build_encoder(cls, kwargs, device="cuda")
+    out = enc(x.cuda())
+    assert out.dtype == torch.float32 and tuple(out.shape) == ref64.shape
+    got = out.cpu().numpy()
+    assert np.isfinite(got).all()
+    emax, erms = err_stats(got, ref64)
+    bmax, brms = err_stats(ref_bf16, ref64)
+    print(f"{name}: ours max {emax:.3e} rms {erms:.3e} | reference bf16-autocast max {bmax:.3e} rms {brms:.3e}")
+    assert emax <= max(bmax, 1e-3) and erms <= max(brms, 1e-4), (emax, erms, bmax, brms)
+    assert emax < 8e-2 and erms < 1.5e-2
+    # second call (packed weights cached) returns the same values in a fresh tensor
+    out2 = enc(x.cuda())
+    assert out2.data_ptr() != out.data_ptr() and torch.equal(out, out2)
+
+
+def test_silu_conv_gemm_matches_torch():
+    """The k=9 'same' convolution + SiLU as a nine-segment GEMM, both kernel families (<=128 rows: single CTA,
+    >128 rows: CTA pair), bf16 and fp32 outputs, against torch fp32 conv1d on the bf16-rounded operands."""
+    import torch.nn.functional as F
+    from naturalspeech2_pytorch_b200 import _lib, ops
+    from naturalspeech2_pytorch_b200.encoders import _conv_segs, _pack_conv
+    g = torch.Generator().manual_seed(3)
+    for rows, c_in, c_out in ((103, 128, 256), (300, 256, 512), (1024, 64, 128)):
+        x = torch.randn(2, rows, c_in, generator=g).bfloat16()
+        w = (torch.randn(c_out, c_in, 9, generator=g) / (9 * c_in) ** 0.5)
+        b = torch.randn(c_out, generator=g) * 0.1
+        ref = F.silu(F.conv1d(x.float().transpose(1, 2), w.bfloat16().float(), b, padding=4)).transpose(1, 2)
+        causal = F.silu(F.conv1d(F.pad(x.float().transpose(1, 2), (8, 0)), w.bfloat16().float(), b)).transpose(1, 2)
+        for dt, epi in ((torch.bfloat16, ops.EPI_BF16), (torch.float32, ops.EPI_F32)):
+            for want, first in ((ref, 4), (causal, 8)):
+                out = torch.empty(2, rows, c_out, device="cuda", dtype=dt)
+                ops.gemm(x.cuda(), _pack_conv(w).cuda(), out, n=c_out, epilogue=epi, segs=_conv_segs(c_in, 9, first),
+                         bias=b.cuda(), flags=_lib.NS2_GEMM_FLAG_SILU)
+                err = (out.float().cpu() - want).abs().max().item()
+                assert err < (2e-2 if dt == torch.bfloat16 else 2e-3), (rows, c_in, c_out, dt, first, err)
+
+
+def test_embedding_bf16():
+    from naturalspeech2_pytorch_b200 import ops
+    g = torch.Generator().manual_seed(4)
+    table = torch.randn(51, 128, generator=g)
+    ids = torch.randint(0, 50, (3, 17), generator=g)
+    ids[2, 10:] = -1
+    out = ops.embedding_bf16(ids.cuda(), table.cuda(), torch.empty(3, 17, 128, device="cuda", dtype=torch.bfloat16), 50)
+    want = table[ids.masked_fill(ids < 0, 50)].bfloat16()
+    assert torch.equal(out.cpu(), want)
