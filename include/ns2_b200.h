@@ -229,6 +229,19 @@ int ns2_transpose_cast(const float* x, int32_t batch, int32_t channels, int32_t 
 int ns2_embedding_bf16(const int64_t* ids, int64_t rows, const float* table, int32_t num_rows, int32_t dim,
                        int32_t pad_id, void* out_bf16, ns2_stream_t stream);
 
+/*    ns2_groupnorm_silu   : y = silu(GroupNorm(groups, channels)(x)) (+ resid) on token-major f32 x (batch, rows, channels):
+ *                           statistics per (batch element, group) over rows x channels/groups values, biased variance,
+ *                           eps inside the square root, per-channel affine (nn.GroupNorm) - Block.forward of the
+ *                           duration / pitch predictor (ns2.py:345-365) with the ResnetBlock residual (ns2.py:399-401).
+ *                           Writes out_f32 and/or out_bf16 (either may be NULL).
+ *    ns2_rowdot           : out[r] = (relu ?) max(0, .) : (.) of dot(x[r,:], w) + bias[0] - Linear(dim, 1) + ReLU heads
+ *                           (ns2.py:452-456) */
+int ns2_groupnorm_silu(const float* x, int32_t batch, int32_t rows, int32_t channels, int32_t groups,
+                       const float* weight, const float* bias, float eps, const float* resid, float* out_f32,
+                       void* out_bf16, ns2_stream_t stream);
+int ns2_rowdot(const float* x, int64_t rows, int32_t dim, const float* w, const float* bias, int32_t relu, float* out,
+               ns2_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * 6. Diffusion element-wise steps, fp32 (NaturalSpeech2.forward ns2.py:1621-1666; ddim_sample 1392-1429).
  *    All take per-sample scalars as device arrays of length `batch`; `per_sample` = N*D elements.

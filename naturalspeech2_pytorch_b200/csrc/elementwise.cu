@@ -389,6 +389,93 @@ __global__ void __launch_bounds__(256) embedding_bf16_kernel(const long long* __
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// GroupNorm + SiLU (+ residual) on token-major activations: Block.forward of the duration / pitch predictor
+// (ns2.py:345-365: Conv1d -> nn.GroupNorm(groups, C) -> SiLU) and the ResnetBlock residual (ns2.py:399-401).
+// One CTA per (group, batch element): statistics over rows x (C/groups) values in three passes over data that
+// stays in L1/L2 (mean, centred variance, apply) - the biased variance and eps placement of nn.GroupNorm.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float block_sum_256(float v, float* red) {
+  v = warp_sum(v);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  float t = (lane < 8) ? red[lane] : 0.f;
+  t = warp_sum(t);
+  return t;
+}
+
+__global__ void __launch_bounds__(256) groupnorm_silu_kernel(const float* __restrict__ x, int rows, int channels,
+                                                             int cpg, const float* __restrict__ weight,
+                                                             const float* __restrict__ bias, float eps,
+                                                             const float* __restrict__ resid,
+                                                             float* __restrict__ out_f32,
+                                                             __nv_bfloat16* __restrict__ out_bf16) {
+  __shared__ float red[8];
+  const int g = blockIdx.x, b = blockIdx.y;
+  const int v4 = cpg / 4;                       // float4 per row of this group
+  const long long base = (static_cast<long long>(b) * rows) * channels + g * cpg;
+  const int total = rows * v4;
+  float s = 0.f;
+  for (int e = threadIdx.x; e < total; e += 256) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(x + base + static_cast<long long>(e / v4) * channels) + e % v4);
+    s += (v.x + v.y) + (v.z + v.w);
+  }
+  const float n = static_cast<float>(rows) * cpg;
+  const float mean = block_sum_256(s, red) / n;
+  float q = 0.f;
+  for (int e = threadIdx.x; e < total; e += 256) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(x + base + static_cast<long long>(e / v4) * channels) + e % v4);
+    const float a = v.x - mean, c = v.y - mean, d = v.z - mean, f = v.w - mean;
+    q += (a * a + c * c) + (d * d + f * f);
+  }
+  const float rstd = rsqrtf(block_sum_256(q, red) / n + eps);
+  for (int e = threadIdx.x; e < total; e += 256) {
+    const int r = e / v4, c4 = e % v4;
+    const long long off = base + static_cast<long long>(r) * channels + c4 * 4;
+    const float4 v = __ldg(reinterpret_cast<const float4*>(x + off));
+    const float4 w = __ldg(reinterpret_cast<const float4*>(weight + g * cpg) + c4);
+    const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + g * cpg) + c4);
+    float y[4] = {(v.x - mean) * rstd * w.x + bb.x, (v.y - mean) * rstd * w.y + bb.y,
+                  (v.z - mean) * rstd * w.z + bb.z, (v.w - mean) * rstd * w.w + bb.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) y[i] = y[i] / (1.0f + __expf(-y[i]));   // SiLU
+    if (resid != nullptr) {
+      const float4 rr = __ldg(reinterpret_cast<const float4*>(resid + off));
+      y[0] += rr.x; y[1] += rr.y; y[2] += rr.z; y[3] += rr.w;
+    }
+    if (out_f32 != nullptr) *reinterpret_cast<float4*>(out_f32 + off) = make_float4(y[0], y[1], y[2], y[3]);
+    if (out_bf16 != nullptr) {
+      uint2 pk;
+      pk.x = pack_bf16x2(y[0], y[1]);
+      pk.y = pack_bf16x2(y[2], y[3]);
+      *reinterpret_cast<uint2*>(out_bf16 + off) = pk;
+    }
+  }
+}
+
+// out[r] = act(dot(x[r, :], w) + bias[0]): the Linear(dim, 1) + ReLU heads of the duration / pitch predictor
+// (ns2.py:452-456).  One warp per row.
+__global__ void __launch_bounds__(256) rowdot_kernel(const float* __restrict__ x, long long rows, int dim,
+                                                     const float* __restrict__ w, const float* __restrict__ bias,
+                                                     int relu, float* __restrict__ out) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long r = static_cast<long long>(blockIdx.x) * 8 + warp;
+  if (r >= rows) return;
+  float s = 0.f;
+  for (int c = lane; c < dim / 4; c += 32) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(x + r * dim) + c);
+    const float4 b = __ldg(reinterpret_cast<const float4*>(w) + c);
+    s += (a.x * b.x + a.y * b.y) + (a.z * b.z + a.w * b.w);
+  }
+  s = warp_sum(s);
+  if (lane == 0) {
+    s += (bias != nullptr) ? __ldg(bias) : 0.f;
+    out[r] = relu ? fmaxf(s, 0.f) : s;
+  }
+}
+
 static cudaError_t configure_small_linear() { return set_max_smem_once(small_linear_kernel, 200 * 1024); }
 
 static unsigned grid_for(long long n4) {
@@ -404,6 +491,40 @@ using namespace ns2;
 extern "C" {
 
 int64_t ns2_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int ns2_groupnorm_silu(const float* x, int32_t batch, int32_t rows, int32_t channels, int32_t groups,
+                       const float* weight, const float* bias, float eps, const float* resid, float* out_f32,
+                       void* out_bf16, ns2_stream_t stream) {
+  NS2_REQUIRE(batch >= 0 && rows >= 0 && channels > 0 && groups > 0 && channels % groups == 0,
+              "groupnorm_silu: bad sizes");
+  NS2_REQUIRE((channels / groups) % 4 == 0, "groupnorm_silu: channels per group (%d) must be a multiple of 4",
+              channels / groups);
+  NS2_REQUIRE(batch <= 65535, "groupnorm_silu: batch %d > 65535", batch);
+  if (batch == 0 || rows == 0) return kOk;
+  NS2_REQUIRE(x && weight && bias && (out_f32 || out_bf16), "groupnorm_silu: null pointer");
+  NS2_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(weight) | reinterpret_cast<uintptr_t>(bias) |
+                reinterpret_cast<uintptr_t>(resid) | reinterpret_cast<uintptr_t>(out_f32)) & 15) == 0 &&
+                  (reinterpret_cast<uintptr_t>(out_bf16) & 7) == 0,
+              "groupnorm_silu: pointers must be 16-byte aligned");
+  groupnorm_silu_kernel<<<dim3(groups, batch), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, rows, channels, channels / groups, weight, bias, eps, resid, out_f32, static_cast<__nv_bfloat16*>(out_bf16));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  NS2_CUDA_CHECK(cudaGetLastError());
+  return kOk;
+}
+
+int ns2_rowdot(const float* x, int64_t rows, int32_t dim, const float* w, const float* bias, int32_t relu, float* out,
+               ns2_stream_t stream) {
+  NS2_REQUIRE(rows >= 0 && dim > 0 && dim % 4 == 0, "rowdot: bad sizes");
+  if (rows == 0) return kOk;
+  NS2_REQUIRE(x && w && out, "rowdot: null pointer");
+  NS2_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w)) & 15) == 0, "rowdot: x and w must be 16-byte aligned");
+  rowdot_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, rows, dim, w, bias,
+                                                                                                  relu, out);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  NS2_CUDA_CHECK(cudaGetLastError());
+  return kOk;
+}
 
 int ns2_embedding_bf16(const int64_t* ids, int64_t rows, const float* table, int32_t num_rows, int32_t dim,
                        int32_t pad_id, void* out_bf16, ns2_stream_t stream) {

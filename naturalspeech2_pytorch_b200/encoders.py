@@ -244,3 +244,161 @@ class PhonemeEncoder(_EncoderBase):
         ops.gemm(e, P["c_w"], h, n=self.dim_hidden, epilogue=ops.EPI_F32,
                  segs=_conv_segs(self.dim, self.kernel_size, self.kernel_size - 1), bias=P["c_b"], flags=_SILU)
         return self._transformer(h, self.transformer, P, self.heads)
+
+
+# --------------------------------------------------------------------------------------------------
+# duration / pitch predictor (ns2.py:345-527)
+# --------------------------------------------------------------------------------------------------
+class _BlockParams(nn.Module):
+    """Block (ns2.py:345-365): proj = Conv1d(k, padding k//2), norm = GroupNorm(groups, dim_out)."""
+
+    def __init__(self, dim, dim_out, kernel, groups):
+        super().__init__()
+        self.proj = nn.Conv1d(dim, dim_out, kernel, padding=kernel // 2)
+        self.norm = nn.GroupNorm(groups, dim_out)
+
+
+class _ResnetBlockParams(nn.Module):
+    """ResnetBlock (ns2.py:367-401) with dim == dim_out (res_conv = Identity, the only shape the trunk builds)."""
+
+    def __init__(self, dim, kernel, groups=8, num_convs=2):
+        super().__init__()
+        self.blocks = nn.Sequential(*[_BlockParams(dim, dim, kernel, groups) for _ in range(num_convs)])
+        self.res_conv = nn.Identity()
+
+
+class _TrunkParams(nn.Module):
+    """DurationPitchPredictorTrunk (ns2.py:412-456)."""
+
+    def __init__(self, dim, depth, kernel_size, dim_context, heads, dim_head, num_convs_per_resnet_block,
+                 num_convolutions_per_block):
+        super().__init__()
+        self.layers = nn.ModuleList([])
+        for _ in range(depth):
+            attn = _AttentionParams(dim, dim_head, heads)
+            if dim_context is not None and dim_context != dim:
+                attn.to_kv = nn.Linear(dim_context, dim_head * heads * 2, bias=False)
+            self.layers.append(nn.ModuleList([
+                nn.Sequential(*[_ResnetBlockParams(dim, kernel_size, num_convs=num_convs_per_resnet_block)
+                                for _ in range(num_convolutions_per_block)]),
+                _RMSNormParams(dim),
+                attn]))
+        self.to_pred = nn.Sequential(nn.Linear(dim, 1), _NoParam(), _NoParam())
+
+
+class DurationPitchPredictor(_EncoderBase):
+    """ns2.py:468-527.  forward(x: (B, T, dim_hidden) phoneme encodings [or (B, T) ids with a token table],
+    encoded_prompts: (B, Np, dim_encoded_prompts)) -> (duration_pred (B, T), pitch_pred (B, T)), both fp32 >= 0."""
+
+    def __init__(self, *, dim, num_phoneme_tokens=None, tokenizer=None, dim_encoded_prompts=None,
+                 num_convolutions_per_block=3, use_resnet_block=True, num_convs_per_resnet_block=2, depth=10,
+                 kernel_size=3, heads=8, dim_head=64, dim_hidden=512, dropout=0.2, use_flash_attn=False):
+        super().__init__()
+        self.tokenizer = tokenizer
+        if num_phoneme_tokens is None and tokenizer is not None:
+            num_phoneme_tokens = tokenizer.vocab_size
+        dim_encoded_prompts = dim if dim_encoded_prompts is None else dim_encoded_prompts
+        if not use_resnet_block:
+            raise NotImplementedError("only the ResnetBlock trunk (the reference default) is built")
+        if kernel_size % 2 != 1 or kernel_size > _lib.NS2_GEMM_MAX_SEGS:
+            raise NotImplementedError("kernel_size must be odd and <= NS2_GEMM_MAX_SEGS")
+        _check_transformer_dims(dim_hidden, dim_head)
+        if dim_encoded_prompts != dim_hidden:
+            # keys = cat(norm(x), encoded_prompts) along the sequence (cross_attn_include_queries, ns2.py:1060-1061)
+            raise NotImplementedError("dim_encoded_prompts must equal dim_hidden (the reference concatenates them)")
+        if num_phoneme_tokens is not None and dim != dim_hidden:
+            raise NotImplementedError("the token table width must equal dim_hidden")
+        self.dim_hidden, self.heads, self.kernel_size = dim_hidden, heads, kernel_size
+        self.phoneme_token_emb = nn.Embedding(num_phoneme_tokens, dim) if num_phoneme_tokens is not None else nn.Identity()
+        mk = lambda: _TrunkParams(dim_hidden, depth, kernel_size, dim_encoded_prompts, heads, dim_head,  # noqa: E731
+                                  num_convs_per_resnet_block, num_convolutions_per_block)
+        self.to_pitch_pred = mk()
+        self.to_duration_pred = mk()
+        self._init_cache()
+
+    def _pack(self) -> Dict[str, torch.Tensor]:
+        P: Dict[str, torch.Tensor] = {}
+        for name, trunk in (("p", self.to_pitch_pred), ("d", self.to_duration_pred)):
+            for l, (convs, norm, attn) in enumerate(trunk.layers):
+                for r, rb in enumerate(convs):
+                    for c, blk in enumerate(rb.blocks):
+                        k = f"{name}{l}_{r}_{c}"
+                        P[k + "_w"] = _pack_conv(blk.proj.weight)
+                        P[k + "_b"] = blk.proj.bias.detach().float().contiguous()
+                        P[k + "_gw"] = blk.norm.weight.detach().float().contiguous()
+                        P[k + "_gb"] = blk.norm.bias.detach().float().contiguous()
+                P[f"{name}{l}_g"] = norm.gamma.detach().float().contiguous()
+                P[f"{name}{l}_q"] = _bf(attn.to_q.weight)
+                P[f"{name}{l}_kv"] = _bf(attn.to_kv.weight)
+                P[f"{name}{l}_o"] = _bf(attn.to_out.weight)
+            P[f"{name}_pw"] = trunk.to_pred[0].weight.detach().float().reshape(-1).contiguous()
+            P[f"{name}_pb"] = trunk.to_pred[0].bias.detach().float().contiguous()
+        if isinstance(self.phoneme_token_emb, nn.Embedding):
+            P["emb"] = self.phoneme_token_emb.weight.detach().float().contiguous()
+        return P
+
+    def _trunk(self, name: str, trunk: _TrunkParams, P, x0: torch.Tensor, prompts_bf: torch.Tensor) -> torch.Tensor:
+        B, T, D = x0.shape
+        Np = prompts_bf.shape[1]
+        dev, bf, H = x0.device, torch.bfloat16, self.heads
+        inner = H * 64
+        groups = trunk.layers[0][0][0].blocks[0].norm.num_groups if len(trunk.layers) else 8
+        eps = trunk.layers[0][0][0].blocks[0].norm.eps if len(trunk.layers) else 1e-5
+        segs = _conv_segs(D, self.kernel_size, self.kernel_size // 2)
+        x = x0.clone()                                               # fp32 stream of this trunk
+        x_bf = ops.cast_bf16(x, torch.empty(B, T, D, device=dev, dtype=bf))
+        c = torch.empty(B, T, D, device=dev, dtype=torch.float32)
+        h_bf = torch.empty(B, T, D, device=dev, dtype=bf)
+        ctx = torch.empty(B, T + Np, D, device=dev, dtype=bf)        # [norm(x) ; encoded prompts] (ns2.py:1060-1061)
+        ctx[:, T:].copy_(prompts_bf)
+        nx = torch.empty(B, T, D, device=dev, dtype=bf)
+        q = torch.empty(B, T, inner, device=dev, dtype=bf)
+        kv = torch.empty(B, T + Np, 2 * inner, device=dev, dtype=bf)
+        o = torch.empty(B, T, inner, device=dev, dtype=bf)
+        for l, (convs, _, _) in enumerate(trunk.layers):
+            for r, rb in enumerate(convs):
+                nb = len(rb.blocks)
+                src = x_bf
+                for ci in range(nb):
+                    k = f"{name}{l}_{r}_{ci}"
+                    ops.gemm(src, P[k + "_w"], c, n=D, epilogue=ops.EPI_F32, segs=segs, bias=P[k + "_b"])
+                    if ci < nb - 1:
+                        ops.groupnorm_silu(c, P[k + "_gw"], P[k + "_gb"], groups, eps=eps, out_bf16=h_bf)
+                        src = h_bf
+                    else:   # out = blocks(x) + res_conv(x), res_conv = Identity (ns2.py:399-401)
+                        ops.groupnorm_silu(c, P[k + "_gw"], P[k + "_gb"], groups, eps=eps, resid=x, out_f32=x,
+                                           out_bf16=x_bf)
+            ops.rmsnorm_film(x, nx, gamma=P[f"{name}{l}_g"])
+            ctx[:, :T].copy_(nx)
+            ops.gemm(nx, P[f"{name}{l}_q"], q, n=inner, epilogue=ops.EPI_BF16)
+            ops.gemm(ctx, P[f"{name}{l}_kv"], kv, n=2 * inner, epilogue=ops.EPI_BF16)
+            ops.attention(q, kv[:, :, :inner], kv[:, :, inner:], o, heads=H)
+            ops.gemm(o, P[f"{name}{l}_o"], x, n=D, epilogue=ops.EPI_F32, resid=x)   # attn(norm(x), prompts) + x
+            ops.cast_bf16(x, x_bf)
+        pred = torch.empty(B, T, device=dev, dtype=torch.float32)
+        ops.rowdot(x, P[f"{name}_pw"], P[f"{name}_pb"], pred, relu=True)            # Linear(dim, 1) + ReLU
+        return pred
+
+    @torch.no_grad()
+    def forward(self, x, encoded_prompts: torch.Tensor, prompt_mask=None):
+        if prompt_mask is not None:
+            raise NotImplementedError("DurationPitchPredictor: prompt masks are not supported by the sm_100a attention kernel")
+        if isinstance(x, (list, tuple)):
+            assert self.tokenizer is not None
+            x = self.tokenizer.texts_to_tensor_ids(x).to(encoded_prompts.device)
+        if not (x.is_cuda and encoded_prompts.is_cuda):
+            raise ValueError("DurationPitchPredictor: inputs must be CUDA tensors (the ns2_b200 ops have no CPU path)")
+        P = self.packed()
+        dev, bf = x.device, torch.bfloat16
+        if "emb" in P:
+            B, T = x.shape
+            e = ops.embedding_bf16(x.long().contiguous(), P["emb"],
+                                   torch.empty(B, T, self.dim_hidden, device=dev, dtype=bf), 0)
+            x = e.float()
+        x = x.float().contiguous()
+        B, Np, Dp = encoded_prompts.shape
+        assert x.shape[-1] == self.dim_hidden and Dp == self.dim_hidden
+        prompts_bf = ops.cast_bf16(encoded_prompts.float().contiguous(), torch.empty(B, Np, Dp, device=dev, dtype=bf))
+        duration = self._trunk("d", self.to_duration_pred, P, x, prompts_bf)
+        pitch = self._trunk("p", self.to_pitch_pred, P, x, prompts_bf)
+        return duration, pitch

@@ -341,6 +341,45 @@ def transpose_cast(x: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
 OBJECTIVES = {"v": _lib.NS2_OBJ_V, "eps": _lib.NS2_OBJ_EPS, "x0": _lib.NS2_OBJ_X0}
 
 
+def groupnorm_silu(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, groups: int, *, eps: float = 1e-5,
+                   resid: Optional[torch.Tensor] = None, out_f32: Optional[torch.Tensor] = None,
+                   out_bf16: Optional[torch.Tensor] = None):
+    """silu(GroupNorm(groups)(x)) (+ resid) for token-major x (B, N, C) f32 -> out_f32 and/or out_bf16 (B, N, C)."""
+    lib = _lib.load()
+    _req(x, torch.float32, "x")
+    _req(weight, torch.float32, "weight")
+    _req(bias, torch.float32, "bias")
+    if x.dim() != 3 or not x.is_contiguous():
+        raise ValueError("x must be a contiguous (B, N, C) tensor")
+    for name, t, dt in (("resid", resid, torch.float32), ("out_f32", out_f32, torch.float32),
+                        ("out_bf16", out_bf16, torch.bfloat16)):
+        if t is not None:
+            _req(t, dt, name)
+            if t.shape != x.shape or not t.is_contiguous():
+                raise ValueError(f"{name} must be contiguous with x's shape")
+    if out_f32 is None and out_bf16 is None:
+        raise ValueError("groupnorm_silu needs at least one output")
+    B, N, Cn = x.shape
+    check(lib.ns2_groupnorm_silu(x.data_ptr(), B, N, Cn, int(groups), weight.data_ptr(), bias.data_ptr(), float(eps),
+                                 _ptr(resid), _ptr(out_f32), _ptr(out_bf16), _stream(x)), "ns2_groupnorm_silu")
+    return out_f32, out_bf16
+
+
+def rowdot(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], out: torch.Tensor, relu: bool = False):
+    """out[...] = (relu)(x[..., :] . w + bias): Linear(dim, 1) heads.  x f32 contiguous, w (dim,), out one value per row."""
+    lib = _lib.load()
+    _req(x, torch.float32, "x")
+    _req(w, torch.float32, "w")
+    _req(out, torch.float32, "out")
+    if not (x.is_contiguous() and w.is_contiguous() and out.is_contiguous()) or out.numel() * x.shape[-1] != x.numel():
+        raise ValueError("rowdot needs contiguous x (..., dim), w (dim,) and one output per row")
+    if bias is not None:
+        _req(bias, torch.float32, "bias")
+    check(lib.ns2_rowdot(x.data_ptr(), out.numel(), x.shape[-1], w.data_ptr(), _ptr(bias), int(relu), out.data_ptr(),
+                         _stream(x)), "ns2_rowdot")
+    return out
+
+
 def embedding_bf16(ids: torch.Tensor, table: torch.Tensor, out: torch.Tensor, pad_id: int) -> torch.Tensor:
     """out[..., :] = bf16(table[ids < 0 ? pad_id : ids]) — nn.Embedding + padding substitution (ns2.py:279-282)."""
     lib = _lib.load()

@@ -270,10 +270,17 @@ ENCODER_CASES = {
     "spe_long": ("SpeechPromptEncoder", dict(dim_codebook=128, dims=(256,), depth=2, heads=4), (1, 300)),
     "spe_full": ("SpeechPromptEncoder", dict(dim_codebook=128, depth=1), (1, 103)),
     "phon_small": ("PhonemeEncoder", dict(num_tokens=50, dim=128, dim_hidden=128, depth=2, heads=2), (2, 37)),
+    # duration / pitch predictor: input = phoneme encodings (B, T, D) and encoded prompts (B, Np, D)
+    "dpp_small": ("DurationPitchPredictor", dict(dim=128, dim_hidden=128, depth=2, heads=2), (2, 37, 50)),
+    "dpp_512": ("DurationPitchPredictor", dict(dim=512, depth=1), (1, 100, 103)),
 }
 
 
 def encoder_inputs(name, cls, kwargs, spec):
+    if cls == "DurationPitchPredictor":
+        B, T, Np = spec
+        D = kwargs.get("dim_hidden", 512)
+        return seeded((B, T, D), 23), seeded((B, Np, D), 24)
     B, T = spec
     if cls == "PhonemeEncoder":
         ids = torch.randint(0, kwargs["num_tokens"], (B, T), generator=torch.Generator().manual_seed(21))
@@ -290,6 +297,24 @@ def encoder_goldens(ns2):
         enc = getattr(ns2, cls)(**kwargs).eval()
         fill_module(enc, seed=1234)
         x = encoder_inputs(name, cls, kwargs, spec)
+        if cls == "DurationPitchPredictor":
+            x, pr = x
+            with torch.no_grad():
+                y32 = torch.stack(enc(x, pr))
+                e64 = getattr(ns2, cls)(**kwargs).double().eval()
+                e64.load_state_dict({k: v.double() for k, v in enc.state_dict().items()})
+                y64 = torch.stack(e64(x.double(), pr.double()))
+                with torch.autocast("cpu", dtype=torch.bfloat16):
+                    y16 = torch.stack(enc(x, pr)).float()
+            print(f"{name}: out mean={y64.mean():.3f} std={y64.std():.3f} zeros={float((y64 == 0).double().mean()):.2f} "
+                  f"|fp32-fp64|max={(y32.double() - y64).abs().max():.2e} "
+                  f"|bf16autocast-fp64|max={(y16.double() - y64).abs().max():.2e}")
+            out[f"{name}_in"] = x.numpy()
+            out[f"{name}_prompts"] = pr.numpy()
+            out[f"{name}_fp64"] = y64.numpy()
+            out[f"{name}_bf16_autocast"] = y16.numpy()
+            out[f"{name}_keys"] = np.array(repr([(k, tuple(v.shape)) for k, v in enc.state_dict().items()]))
+            continue
         with torch.no_grad():
             y32 = enc(x)
             e64 = getattr(ns2, cls)(**kwargs).double().eval()

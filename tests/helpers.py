@@ -80,6 +80,7 @@ def aligner_golden_cases():
 
 
 ENCODER_CASES = ["spe_small", "spe_long", "spe_full", "phon_small"]
+DPP_CASES = ["dpp_small", "dpp_512"]
 
 
 def encoder_case(name: str):
@@ -96,3 +97,13 @@ def build_encoder(cls: str, kwargs: dict, seed: int = 1234, device="cpu"):
     m = getattr(encoders, cls)(**kwargs)
     fill_module(m, seed)
     return m.to(device).eval()
+
+
+def dpp_case(name: str):
+    """(ctor kwargs, phoneme encodings, encoded prompts, fp64 reference (2, B, T), reference autocast-bf16, key list)."""
+    from golden.make_golden import ENCODER_CASES as SPEC
+    z = np.load(GOLDEN / "encoders.npz")
+    _, kwargs, _ = SPEC[name]
+    keys = ast.literal_eval(str(z[f"{name}_keys"]))
+    return (dict(kwargs), torch.from_numpy(z[f"{name}_in"]), torch.from_numpy(z[f"{name}_prompts"]), z[f"{name}_fp64"],
+            z[f"{name}_bf16_autocast"], keys)

@@ -3,7 +3,7 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import ENCODER_CASES, build_encoder, encoder_case
+from helpers import DPP_CASES, ENCODER_CASES, build_encoder, dpp_case, encoder_case
 
 
 @pytest.mark.parametrize("name", ENCODER_CASES)
@@ -37,3 +37,14 @@ def test_encoders_reject_cpu_inputs_and_masks():
     cls, kwargs, x, *_ = encoder_case("spe_small")
     with pytest.raises(ValueError):
         build_encoder(cls, kwargs)(x)
+
+
+@pytest.mark.parametrize("name", DPP_CASES)
+def test_duration_pitch_oracle_and_state_dict(name):
+    from oracle import encoders_oracle
+    kwargs, x, prompts, ref64, _, keys = dpp_case(name)
+    enc = build_encoder("DurationPitchPredictor", kwargs)
+    assert [(k, tuple(v.shape)) for k, v in enc.state_dict().items()] == [(k, tuple(s)) for k, s in keys]
+    P = {k: v.double() for k, v in enc.state_dict().items()}
+    dur, pitch = encoders_oracle.duration_pitch_predictor(P, x.double(), prompts.double(), heads=kwargs.get("heads", 8))
+    assert np.abs(torch.stack((dur, pitch)).numpy() - ref64).max() < 1e-9

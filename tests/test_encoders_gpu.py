@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import ENCODER_CASES, build_encoder, encoder_case, err_stats
+from helpers import DPP_CASES, ENCODER_CASES, build_encoder, dpp_case, encoder_case, err_stats
 
 pytestmark = pytest.mark.gpu
 
@@ -59,3 +59,39 @@ def test_embedding_bf16():
     out = ops.embedding_bf16(ids.cuda(), table.cuda(), torch.empty(3, 17, 128, device="cuda", dtype=torch.bfloat16), 50)
     want = table[ids.masked_fill(ids < 0, 50)].bfloat16()
     assert torch.equal(out.cpu(), want)
+
+
+@pytest.mark.parametrize("name", DPP_CASES)
+def test_duration_pitch_predictor_matches_reference_golden(name):
+    kwargs, x, prompts, ref64, ref_bf16, _ = dpp_case(name)
+    enc = build_encoder("DurationPitchPredictor", kwargs, device="cuda")
+    dur, pitch = enc(x.cuda(), prompts.cuda())
+    got = torch.stack((dur, pitch)).cpu().numpy()
+    assert got.shape == ref64.shape and np.isfinite(got).all() and (got >= 0).all()
+    emax, erms = err_stats(got, ref64)
+    bmax, brms = err_stats(ref_bf16, ref64)
+    print(f"{name}: ours max {emax:.3e} rms {erms:.3e} | reference bf16-autocast max {bmax:.3e} rms {brms:.3e}")
+    assert emax <= max(bmax, 1e-3) and erms <= max(brms, 1e-4), (emax, erms, bmax, brms)
+    assert emax < 5e-2 and erms < 1e-2
+
+
+def test_groupnorm_silu_and_rowdot_match_torch():
+    import torch.nn.functional as F
+    from naturalspeech2_pytorch_b200 import ops
+    g = torch.Generator().manual_seed(6)
+    for B, N, Cn, G in ((2, 37, 128, 8), (3, 100, 512, 8), (1, 5, 64, 4)):
+        x = torch.randn(B, N, Cn, generator=g) * 2 + 0.5
+        w, b = torch.randn(Cn, generator=g), torch.randn(Cn, generator=g)
+        r = torch.randn(B, N, Cn, generator=g)
+        want = F.silu(F.group_norm(x.double().transpose(1, 2), G, w.double(), b.double(), 1e-5)).transpose(1, 2)
+        o32 = torch.empty(B, N, Cn, device="cuda")
+        obf = torch.empty(B, N, Cn, device="cuda", dtype=torch.bfloat16)
+        ops.groupnorm_silu(x.cuda(), w.cuda(), b.cuda(), G, out_f32=o32, out_bf16=obf)
+        assert (o32.cpu().double() - want).abs().max() < 2e-5
+        assert (obf.cpu().double() - want).abs().max() < 4e-2
+        xr = r.clone().cuda()                                     # in-place residual: out aliases resid
+        ops.groupnorm_silu(x.cuda(), w.cuda(), b.cuda(), G, resid=xr, out_f32=xr)
+        assert (xr.cpu().double() - (want + r.double())).abs().max() < 2e-5
+        wv, bias = torch.randn(Cn, generator=g), torch.randn(1, generator=g)
+        out = ops.rowdot(x.cuda(), wv.cuda(), bias.cuda(), torch.empty(B, N, device="cuda"), relu=True)
+        assert (out.cpu().double() - F.relu(x.double() @ wv.double() + bias.double())).abs().max() < 1e-4
