@@ -241,6 +241,14 @@ int ns2_groupnorm_silu(const float* x, int32_t batch, int32_t rows, int32_t chan
                        void* out_bf16, ns2_stream_t stream);
 int ns2_rowdot(const float* x, int64_t rows, int32_t dim, const float* w, const float* bias, int32_t relu, float* out,
                ns2_stream_t stream);
+/*    ns2_expand_encodings : length regulation, NaturalSpeech2.expand_encodings (ns2.py:1449-1455) with the hard alignment
+ *                           given as one text index per frame: out[b, d, n] = phon[b, m, d] + pitch_table[coarse[b, m], d],
+ *                           m = idx[b, n] (int32; negative = frame past the sample's length -> 0).  phon f32 (batch, t_text,
+ *                           dim) token-major, coarse int32 (batch, t_text) = f0_to_coarse bins, out f32 (batch, dim, length)
+ *                           channel-first (the `cond` layout of Model.forward, ns2.py:929-937). */
+int ns2_expand_encodings(const float* phon, const int32_t* coarse, const float* pitch_table, int32_t table_rows,
+                         const int32_t* idx, int32_t batch, int32_t t_text, int32_t dim, int32_t length, float* out,
+                         ns2_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * 6. Diffusion element-wise steps, fp32 (NaturalSpeech2.forward ns2.py:1621-1666; ddim_sample 1392-1429).

@@ -10,5 +10,7 @@ from .diffusion import NaturalSpeech2  # noqa: F401
 from .codec import EncodecRVQ  # noqa: F401
 from . import parallel  # noqa: F401
 from .aligner import maximum_path  # noqa: F401
+from .encoders import (Conditioner, DurationPitchPredictor, PhonemeEncoder,  # noqa: F401
+                       SpeechPromptEncoder)
 
 __version__ = "0.1.0"

@@ -100,6 +100,7 @@ SIGNATURES = {
     "ns2_transpose_cast": (C.c_int, [_P, _I32, _I32, _I32, _P, _P]),
     "ns2_groupnorm_silu": (C.c_int, [_P, _I32, _I32, _I32, _I32, _P, _P, _F, _P, _P, _P, _P]),
     "ns2_rowdot": (C.c_int, [_P, _I64, _I32, _P, _P, _I32, _P, _P]),
+    "ns2_expand_encodings": (C.c_int, [_P, _P, _P, _I32, _P, _I32, _I32, _I32, _I32, _P, _P]),
     "ns2_embedding_bf16": (C.c_int, [_P, _I64, _P, _I32, _I32, _I32, _P, _P]),
     "ns2_cond_inject": (C.c_int, [_P, _P, _P, _P, _I32, _I32, _I32, _I32, _P, _P]),
     "ns2_select_rows": (C.c_int, [_P, _P, _P, _I64, _I32, _I32, _P, _I64, _I32, _P]),

@@ -476,6 +476,41 @@ __global__ void __launch_bounds__(256) rowdot_kernel(const float* __restrict__ x
   }
 }
 
+// Length regulation of the conditional path: expand_encodings (ns2.py:1449-1455) with the 0/1 alignment given as one
+// text index per frame.  out[b, d, n] = phon[b, m, d] + pitch_table[coarse[b, m], d] with m = idx[b, n]; 0 where
+// idx < 0 (frames past the sample's length).  Output is channel-first (B, D, L) like the reference's `cond`;
+// 32 x 32 tiles go through shared memory so both the gathers (along d) and the stores (along n) are coalesced.
+__global__ void __launch_bounds__(256) expand_encodings_kernel(const float* __restrict__ phon,
+                                                               const int* __restrict__ coarse,
+                                                               const float* __restrict__ table, int table_rows,
+                                                               const int* __restrict__ idx, int T, int D, int L,
+                                                               float* __restrict__ out) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z, n0 = blockIdx.x * 32, d0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+#pragma unroll
+  for (int r = ty; r < 32; r += 8) {
+    const int n = n0 + r, d = d0 + tx;
+    float v = 0.f;
+    if (n < L && d < D) {
+      const int m = __ldg(idx + static_cast<long long>(b) * L + n);
+      if (m >= 0 && m < T) {
+        int c = __ldg(coarse + static_cast<long long>(b) * T + m);
+        c = c < 0 ? 0 : (c >= table_rows ? table_rows - 1 : c);
+        v = __fadd_rn(__ldg(phon + (static_cast<long long>(b) * T + m) * D + d),
+                      __ldg(table + static_cast<long long>(c) * D + d));
+      }
+    }
+    tile[r][tx] = v;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = ty; r < 32; r += 8) {
+    const int d = d0 + r, n = n0 + tx;
+    if (d < D && n < L) out[(static_cast<long long>(b) * D + d) * L + n] = tile[tx][r];
+  }
+}
+
 static cudaError_t configure_small_linear() { return set_max_smem_once(small_linear_kernel, 200 * 1024); }
 
 static unsigned grid_for(long long n4) {
@@ -521,6 +556,22 @@ int ns2_rowdot(const float* x, int64_t rows, int32_t dim, const float* w, const 
   NS2_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w)) & 15) == 0, "rowdot: x and w must be 16-byte aligned");
   rowdot_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, rows, dim, w, bias,
                                                                                                   relu, out);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  NS2_CUDA_CHECK(cudaGetLastError());
+  return kOk;
+}
+
+int ns2_expand_encodings(const float* phon, const int32_t* coarse, const float* pitch_table, int32_t table_rows,
+                         const int32_t* idx, int32_t batch, int32_t t_text, int32_t dim, int32_t length, float* out,
+                         ns2_stream_t stream) {
+  NS2_REQUIRE(batch >= 0 && t_text > 0 && dim > 0 && length >= 0 && table_rows > 0, "expand_encodings: bad sizes");
+  NS2_REQUIRE(batch <= 65535, "expand_encodings: batch %d > 65535", batch);
+  if (batch == 0 || length == 0) return kOk;
+  NS2_REQUIRE(phon && coarse && pitch_table && idx && out, "expand_encodings: null pointer");
+  const dim3 grid((length + 31) / 32, (dim + 31) / 32, batch);
+  NS2_REQUIRE(grid.y <= 65535, "expand_encodings: dim too large");
+  expand_encodings_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(phon, coarse, pitch_table, table_rows, idx,
+                                                                              t_text, dim, length, out);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   NS2_CUDA_CHECK(cudaGetLastError());
   return kOk;

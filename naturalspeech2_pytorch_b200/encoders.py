@@ -402,3 +402,65 @@ class DurationPitchPredictor(_EncoderBase):
         duration = self._trunk("d", self.to_duration_pred, P, x, prompts_bf)
         pitch = self._trunk("p", self.to_pitch_pred, P, x, prompts_bf)
         return duration, pitch
+
+
+# --------------------------------------------------------------------------------------------------
+# the conditional front end of NaturalSpeech2.sample (ns2.py:1472-1483)
+# --------------------------------------------------------------------------------------------------
+def f0_to_coarse(f0: torch.Tensor, f0_bin: int = 256, f0_max: float = 1100.0, f0_min: float = 50.0) -> torch.Tensor:
+    """ns2.py:164-177 — (B, T)-sized host-side glue kept in torch like the noise schedules."""
+    f0_mel_max = 1127 * torch.log(1 + torch.tensor(f0_max) / 700)
+    f0_mel_min = 1127 * torch.log(1 + torch.tensor(f0_min) / 700)
+    f0_mel = 1127 * (1 + f0 / 700).log()
+    pos = f0_mel > 0
+    f0_mel = torch.where(pos, (f0_mel - f0_mel_min) * (f0_bin - 2) / (f0_mel_max - f0_mel_min) + 1, f0_mel)
+    f0_mel = f0_mel.clamp(min=1, max=f0_bin - 1)
+    return (f0_mel + 0.5).int()
+
+
+def frames_to_text_index(duration: torch.Tensor) -> torch.Tensor:
+    """The hard alignment of generate_mask_from_repeats (ns2.py:87-104) as one text index per frame: (B, L) int32,
+    L = max total duration, -1 past a sample's own length.  mask[b, i, n] of the reference == (idx[b, n] == i)."""
+    repeats = duration.int()
+    cumsum = repeats.cumsum(dim=-1)
+    lengths = cumsum[:, -1]
+    L = int(lengths.amax().item())
+    seq = torch.arange(L, device=duration.device).unsqueeze(0).expand(duration.shape[0], L).contiguous()
+    idx = torch.searchsorted(cumsum, seq, right=True)          # first i with cumsum[i] > n
+    idx = torch.where(seq < lengths.unsqueeze(-1), idx, torch.full_like(idx, -1))
+    return idx.int().contiguous()
+
+
+def expand_encodings(phoneme_enc: torch.Tensor, duration: torch.Tensor, pitch: torch.Tensor,
+                     pitch_table: torch.Tensor) -> torch.Tensor:
+    """cond (B, D, L) of ns2.py:1478-1483: phoneme encodings + coarse-pitch embeddings repeated `duration` frames."""
+    idx = frames_to_text_index(duration)
+    coarse = f0_to_coarse(pitch.float()).contiguous()
+    return ops.expand_encodings(phoneme_enc.float().contiguous(), coarse, pitch_table.detach().float().contiguous(), idx)
+
+
+class Conditioner(nn.Module):
+    """The per-sample conditional front end of `NaturalSpeech2.sample` (ns2.py:1472-1483) as the `conditioner`
+    callable of `naturalspeech2_pytorch_b200.NaturalSpeech2`: prompt latents + phoneme ids -> (prompt_enc, cond).
+    Sub-module names follow the reference's NaturalSpeech2 attributes (ns2.py:1231-1236), so the matching slices of a
+    reference checkpoint load with `load_state_dict(..., strict=False)`.  The training-time front end (mel, pitch
+    extraction, aligner network, ns2.py:1537-1583) is not built: `mode="train"` raises."""
+
+    def __init__(self, *, dim_codebook=128, num_phoneme_tokens=None, tokenizer=None, duration_pitch_dim=512,
+                 pitch_emb_dim=256, pitch_emb_pp_hidden_dim=512):
+        super().__init__()
+        self.phoneme_enc = PhonemeEncoder(tokenizer=tokenizer, num_tokens=num_phoneme_tokens)
+        self.prompt_enc = SpeechPromptEncoder(dim_codebook=dim_codebook)
+        self.duration_pitch = DurationPitchPredictor(dim=duration_pitch_dim)
+        self.pitch_emb = nn.Embedding(pitch_emb_dim, pitch_emb_pp_hidden_dim)
+
+    @torch.no_grad()
+    def forward(self, prompt=None, text=None, text_lens=None, mode="sample", **unused):
+        if mode != "sample":
+            raise NotImplementedError("Conditioner: only the sampling front end (ns2.py:1472-1483) is built")
+        assert prompt is not None and text is not None
+        prompt_enc = self.prompt_enc(prompt)
+        phoneme_enc = self.phoneme_enc(text)
+        duration, pitch = self.duration_pitch(phoneme_enc, prompt_enc)
+        cond = expand_encodings(phoneme_enc, duration, pitch, self.pitch_emb.weight)
+        return prompt_enc, cond

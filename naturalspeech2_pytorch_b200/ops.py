@@ -380,6 +380,26 @@ def rowdot(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], out: 
     return out
 
 
+def expand_encodings(phon: torch.Tensor, coarse: torch.Tensor, pitch_table: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+    """(B, D, L) f32 channel-first: phon[b, idx[b, n], :] + pitch_table[coarse[b, idx[b, n]], :], 0 where idx < 0
+    (expand_encodings, ns2.py:1449-1455).  phon (B, T, D) f32, coarse (B, T) int32, idx (B, L) int32."""
+    lib = _lib.load()
+    _req(phon, torch.float32, "phon")
+    _req(pitch_table, torch.float32, "pitch_table")
+    _req(coarse, torch.int32, "coarse")
+    _req(idx, torch.int32, "idx")
+    if not all(t.is_contiguous() for t in (phon, coarse, pitch_table, idx)):
+        raise ValueError("expand_encodings needs contiguous tensors")
+    B, T, D = phon.shape
+    if coarse.shape != (B, T) or idx.dim() != 2 or idx.shape[0] != B or pitch_table.shape[1] != D:
+        raise ValueError("expand_encodings: inconsistent shapes")
+    L = idx.shape[1]
+    out = torch.empty(B, D, L, device=phon.device, dtype=torch.float32)
+    check(lib.ns2_expand_encodings(phon.data_ptr(), coarse.data_ptr(), pitch_table.data_ptr(), pitch_table.shape[0],
+                                   idx.data_ptr(), B, T, D, L, out.data_ptr(), _stream(phon)), "ns2_expand_encodings")
+    return out
+
+
 def embedding_bf16(ids: torch.Tensor, table: torch.Tensor, out: torch.Tensor, pad_id: int) -> torch.Tensor:
     """out[..., :] = bf16(table[ids < 0 ? pad_id : ids]) — nn.Embedding + padding substitution (ns2.py:279-282)."""
     lib = _lib.load()

@@ -328,6 +328,21 @@ def encoder_goldens(ns2):
         out[f"{name}_fp64"] = y64.numpy()
         out[f"{name}_bf16_autocast"] = y16.numpy()
         out[f"{name}_keys"] = np.array(repr([(k, tuple(v.shape)) for k, v in enc.state_dict().items()]))
+    # length regulation (ns2.py:87-104, 164-177, 1449-1455) with the reference's own functions
+    g = torch.Generator().manual_seed(31)
+    ph = torch.randn(3, 21, 64, generator=g)
+    dur = torch.rand(3, 21, generator=g) * 5
+    dur[1, 12:] = 0
+    dur[2] = dur[2] * 0.3
+    pitch = torch.rand(3, 21, generator=g) * 900
+    pitch[0, :4] = 0
+    table = torch.randn(256, 64, generator=g)
+    attn = ns2.generate_mask_from_repeats(dur).float()
+    fake = types.SimpleNamespace(pitch_emb=lambda ids: table[ids.long()])
+    cond = ns2.NaturalSpeech2.expand_encodings(fake, ph.transpose(1, 2), attn.unsqueeze(1), pitch.unsqueeze(1).clone())
+    out.update(expand_phon=ph.numpy(), expand_duration=dur.numpy(), expand_pitch=pitch.numpy(), expand_table=table.numpy(),
+               expand_cond=cond.numpy())
+    print("expand:", tuple(cond.shape))
     np.savez_compressed(HERE / "encoders.npz", **out)
 
 

@@ -48,3 +48,18 @@ def test_duration_pitch_oracle_and_state_dict(name):
     P = {k: v.double() for k, v in enc.state_dict().items()}
     dur, pitch = encoders_oracle.duration_pitch_predictor(P, x.double(), prompts.double(), heads=kwargs.get("heads", 8))
     assert np.abs(torch.stack((dur, pitch)).numpy() - ref64).max() < 1e-9
+
+
+def test_length_regulation_oracle_and_host_glue_match_reference():
+    """generate_mask_from_repeats / f0_to_coarse / expand_encodings: oracle == reference golden (bit-exact), and the
+    product's torch glue (frame -> text index, coarse pitch bins) reproduces the reference's hard alignment."""
+    from helpers import GOLDEN
+    from naturalspeech2_pytorch_b200.encoders import f0_to_coarse, frames_to_text_index
+    from oracle import encoders_oracle
+    z = np.load(GOLDEN / "encoders.npz")
+    ph, dur, pitch, table = (torch.from_numpy(z[f"expand_{k}"]) for k in ("phon", "duration", "pitch", "table"))
+    np.testing.assert_array_equal(encoders_oracle.expand_encodings(ph, dur, pitch, table).numpy(), z["expand_cond"])
+    idx = frames_to_text_index(dur)
+    mask = encoders_oracle.generate_mask_from_repeats(dur)
+    assert torch.equal(mask, idx.unsqueeze(1) == torch.arange(dur.shape[1]).view(1, -1, 1))
+    assert torch.equal(f0_to_coarse(pitch), encoders_oracle.f0_to_coarse(pitch))

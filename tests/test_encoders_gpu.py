@@ -95,3 +95,40 @@ def test_groupnorm_silu_and_rowdot_match_torch():
         wv, bias = torch.randn(Cn, generator=g), torch.randn(1, generator=g)
         out = ops.rowdot(x.cuda(), wv.cuda(), bias.cuda(), torch.empty(B, N, device="cuda"), relu=True)
         assert (out.cpu().double() - F.relu(x.double() @ wv.double() + bias.double())).abs().max() < 1e-4
+
+
+def test_expand_encodings_bit_exact():
+    from helpers import GOLDEN
+    from naturalspeech2_pytorch_b200.encoders import expand_encodings
+    z = np.load(GOLDEN / "encoders.npz")
+    ph, dur, pitch, table = (torch.from_numpy(z[f"expand_{k}"]).cuda() for k in ("phon", "duration", "pitch", "table"))
+    cond = expand_encodings(ph, dur, pitch, table)
+    np.testing.assert_array_equal(cond.cpu().numpy(), z["expand_cond"])
+
+
+def test_conditioner_drives_conditional_sampling():
+    """prompt latents + phoneme ids -> (prompt_enc, cond) -> NaturalSpeech2.sample (the flow of ns2.py:1472-1493)."""
+    from naturalspeech2_pytorch_b200 import Model, NaturalSpeech2
+    from naturalspeech2_pytorch_b200.encoders import Conditioner, expand_encodings
+    torch.manual_seed(0)
+    cond_net = Conditioner(dim_codebook=128, num_phoneme_tokens=50).cuda().eval()
+    with torch.no_grad():
+        for trunk in (cond_net.duration_pitch.to_duration_pred, cond_net.duration_pitch.to_pitch_pred):
+            trunk.to_pred[0].bias.fill_(3.0)     # random-init heads predict ~0 frames per phoneme otherwise
+    g = torch.Generator().manual_seed(1)
+    prompt = torch.randn(2, 103, 128, generator=g).cuda()
+    text = torch.randint(0, 50, (2, 23), generator=g).cuda()
+    prompt_enc, cond = cond_net(prompt=prompt, text=text, mode="sample")
+    assert prompt_enc.shape == (2, 103, 512) and cond.shape[:2] == (2, 512) and cond.shape[2] > 0
+    assert torch.isfinite(prompt_enc).all() and torch.isfinite(cond).all()
+    # the composite equals its parts
+    ph = cond_net.phoneme_enc(text)
+    dur, pitch = cond_net.duration_pitch(ph, prompt_enc)
+    assert torch.equal(cond, expand_encodings(ph, dur, pitch, cond_net.pitch_emb.weight))
+    model = Model(dim=128, depth=1, heads=2, wavenet_layers=2, wavenet_stacks=1, dim_prompt=512,
+                  condition_on_prompt=True).cuda().eval()
+    ns = NaturalSpeech2(model, target_sample_hz=24000, timesteps=2, conditioner=cond_net)
+    out = ns.sample(length=64, prompt=prompt, text=text)
+    assert out.shape == (2, 64, 128) and torch.isfinite(out).all()
+    with pytest.raises(NotImplementedError):
+        cond_net(prompt=prompt, text=text, mode="train")
