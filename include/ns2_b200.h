@@ -330,7 +330,7 @@ int ns2_rvq_ce(const float* frames, int64_t num_frames, int32_t d, const float* 
  *    ns2_colsum_bf16      : out[c] += sum_r t[r, c]            (bias gradients)
  *    ns2_group_sum_bf16   : out[r, c] = sum_g t[r, g*dim + c]  (gradient of an input shared by all dilation columns)
  *    ns2_mse_bwd          : out = coef[b] * (pred - target), bf16 and/or f32   (seed of the backward pass, ns2.py:1646-1666)
- *    ns2_film_wgrad       : dw[r, c] += sum_b dfilm[b, r] * t[b, c]  (FiLM projection weights; batch <= 48 per call)
+ *    ns2_film_wgrad       : dw[r, c] (+)= sum_b dfilm[b, r] * t[b, c]  (FiLM projection weights; batch <= 32 per call)
  *    ns2_attn_bwd         : flash-attention backward (dq, dk, dv) from (q, k, v, o, lse, do)
  * ------------------------------------------------------------------------------------------------ */
 int ns2_rmsnorm_film_bwd(const float* x, const void* dh_bf16, int64_t rows, int32_t dim, int32_t rows_per_batch,
@@ -346,7 +346,7 @@ int ns2_group_sum_bf16(const void* t_bf16, int64_t rows, int32_t dim, int32_t gr
 int ns2_mse_bwd(const float* pred, const float* target, const float* coef, int32_t batch, int64_t per_sample,
                 void* out_bf16 /* optional */, float* out_f32 /* optional */, ns2_stream_t stream);
 int ns2_film_wgrad(const float* dfilm, const float* t, int32_t batch, int64_t rows, int32_t cols, float* dw,
-                   ns2_stream_t stream);
+                   int32_t accumulate /* 0: dw = ..., dw need not be initialised; 1: dw += ... */, ns2_stream_t stream);
 /*    ns2_accum_bf16       : acc (f32) += t (bf16); acc_bf16 (optional) = bf16(acc)   (joins a branch gradient) */
 int ns2_accum_bf16(float* acc, const void* t_bf16, int64_t count, void* acc_bf16, ns2_stream_t stream);
 

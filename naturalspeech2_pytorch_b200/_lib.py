@@ -115,7 +115,7 @@ SIGNATURES = {
     "ns2_colsum_bf16": (C.c_int, [_P, _I64, _I32, _I64, _P, _P]),
     "ns2_group_sum_bf16": (C.c_int, [_P, _I64, _I32, _I32, _P, _P]),
     "ns2_mse_bwd": (C.c_int, [_P, _P, _P, _I32, _I64, _P, _P, _P]),
-    "ns2_film_wgrad": (C.c_int, [_P, _P, _I32, _I64, _I32, _P, _P]),
+    "ns2_film_wgrad": (C.c_int, [_P, _P, _I32, _I64, _I32, _P, _I32, _P]),
     "ns2_accum_bf16": (C.c_int, [_P, _P, _I64, _P, _P]),
     "ns2_rvq_prepare": (C.c_int, [_P, _I32, _I32, _I32, _P, _P, _P, _P]),
     "ns2_rvq_encode": (C.c_int, [_P, _I64, _I32, _P, _P, _P, _P, _I32, _I32, _P, _P, _P]),

@@ -172,68 +172,67 @@ __global__ void __launch_bounds__(256) geglu_bwd_kernel(uint32_t* __restrict__ p
 //   dz = dy * [(1 - tanh^2) sigmoid + tanh sigmoid (1 - sigmoid)];  dc = dz * fg;  d fg += sum_rows dz * c;  d fb += sum_rows dz
 // c: conv output incl. bias (recomputed), (B, N, G*D) bf16; dy: (B, N, G*D) bf16 view (row stride dy_rs);
 // dc written to (B, N, G*D) bf16 view (row stride dc_rs).  film / dfilm: per batch, group g at g*film_gs: [gamma | beta].
-// One CTA = 32 rows of one batch x one group.
+// One CTA = 64 rows of one batch x one group (two rows of every warp in flight at once).
 // ------------------------------------------------------------------------------------------------
-template <int VEC>
+// Thread layout: a thread owns ONE quad of channels and walks the rows of its row lane (256 / (dim/4) row lanes per
+// CTA), four rows in flight at a time - few registers, many CTAs per SM, so enough loads are outstanding to stream
+// the three (B, N, G*D) bf16 tensors near HBM speed (the previous one-row-per-warp layout reached 2 TB/s).
 __global__ void __launch_bounds__(256) wavenet_gate_bwd_kernel(const uint2* __restrict__ c, long long c_rs4,
                                                                const uint2* __restrict__ dy, long long dy_rs4,
                                                                uint2* __restrict__ dc, long long dc_rs4, int rows_per_batch,
                                                                int dim, int groups, const float* __restrict__ film,
                                                                long long film_bs, int film_gs, float* __restrict__ dfilm,
                                                                long long dfilm_bs) {
-  __shared__ float red[8][VEC * 128];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int chunks = (rows_per_batch + 31) / 32;
+  extern __shared__ __align__(16) float gate_red[];   // [row lanes][dim]
+  const int Q = dim / 4, RL = 256 / Q;
+  const int q = threadIdx.x % Q, rl = threadIdx.x / Q;
+  const int chunks = (rows_per_batch + 63) / 64;
   int idx = blockIdx.x;
   const int g = idx % groups;
   idx /= groups;
   const int b = idx / chunks;
-  const int r0 = (idx - b * chunks) * 32;
+  const int r0 = (idx - b * chunks) * 64;
+  const int nrows = min(64, rows_per_batch - r0);
   const float* fgp = film + b * film_bs + g * film_gs;
-  float4 fg[VEC], acc_g[VEC], acc_b[VEC];
-#pragma unroll
-  for (int i = 0; i < VEC; ++i) {
-    fg[i] = __ldg(reinterpret_cast<const float4*>(fgp) + i * 32 + lane);
-    acc_g[i] = acc_b[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-  }
-  for (int rr = warp; rr < 32; rr += 8) {
-    const int r = r0 + rr;
-    if (r >= rows_per_batch) break;
-    const long long row = static_cast<long long>(b) * rows_per_batch + r;
-#pragma unroll
-    for (int i = 0; i < VEC; ++i) {
-      const int c4 = g * (dim / 4) + i * 32 + lane;
-      const float4 fb = __ldg(reinterpret_cast<const float4*>(fgp + dim) + i * 32 + lane);
+  const float4 fg4 = __ldg(reinterpret_cast<const float4*>(fgp) + q);
+  const float4 fb4 = __ldg(reinterpret_cast<const float4*>(fgp + dim) + q);
+  const float ga[4] = {fg4.x, fg4.y, fg4.z, fg4.w}, be[4] = {fb4.x, fb4.y, fb4.z, fb4.w};
+  float acc_g[4] = {0.f, 0.f, 0.f, 0.f}, acc_b[4] = {0.f, 0.f, 0.f, 0.f};
+  const int c4 = g * Q + q;
+  if (rl < RL) {
+#pragma unroll 4
+    for (int rr = rl; rr < nrows; rr += RL) {
+      const long long row = static_cast<long long>(b) * rows_per_batch + r0 + rr;
       const uint2 cw = __ldg(c + row * c_rs4 + c4), dw = __ldg(dy + row * dy_rs4 + c4);
       const float2 c01 = bf2_to_f2(cw.x), c23 = bf2_to_f2(cw.y), d01 = bf2_to_f2(dw.x), d23 = bf2_to_f2(dw.y);
       const float cv[4] = {c01.x, c01.y, c23.x, c23.y}, dv[4] = {d01.x, d01.y, d23.x, d23.y};
-      const float ga[4] = {fg[i].x, fg[i].y, fg[i].z, fg[i].w}, be[4] = {fb.x, fb.y, fb.z, fb.w};
-      float o[4], dz[4];
+      float o[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const float z = fmaf(cv[j], ga[j], be[j]);
-        const float th = tanhf(z), sg = 1.0f / (1.0f + expf(-z));
-        dz[j] = dv[j] * ((1.0f - th * th) * sg + th * sg * (1.0f - sg));
-        o[j] = dz[j] * ga[j];
+        // one exponential per element: u = e^-z, sigmoid = 1/(1+u), tanh = (1-u^2)/(1+u^2); |z| clamped where both
+        // have saturated to fp32 precision
+        const float z = fminf(fmaxf(fmaf(cv[j], ga[j], be[j]), -20.0f), 20.0f);
+        const float u = __expf(-z), u2 = u * u;
+        const float sg = __fdividef(1.0f, 1.0f + u);
+        const float th = (1.0f - u2) * __fdividef(1.0f, 1.0f + u2);
+        const float dz = dv[j] * ((1.0f - th * th) * sg + th * sg * (1.0f - sg));
+        o[j] = dz * ga[j];
+        acc_g[j] = fmaf(dz, cv[j], acc_g[j]);
+        acc_b[j] += dz;
       }
       dc[row * dc_rs4 + c4] = make_uint2(f2_to_bf2(o[0], o[1]), f2_to_bf2(o[2], o[3]));
-      acc_g[i].x += dz[0] * cv[0]; acc_g[i].y += dz[1] * cv[1]; acc_g[i].z += dz[2] * cv[2]; acc_g[i].w += dz[3] * cv[3];
-      acc_b[i].x += dz[0]; acc_b[i].y += dz[1]; acc_b[i].z += dz[2]; acc_b[i].w += dz[3];
     }
   }
   for (int pass = 0; pass < 2; ++pass) {
     __syncthreads();
-#pragma unroll
-    for (int i = 0; i < VEC; ++i) {
-      const float4 v = pass == 0 ? acc_g[i] : acc_b[i];
-      float* dst = &red[warp][(i * 32 + lane) * 4];
-      dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
+    if (rl < RL) {
+      const float* v = pass == 0 ? acc_g : acc_b;
+      *reinterpret_cast<float4*>(gate_red + rl * dim + 4 * q) = make_float4(v[0], v[1], v[2], v[3]);
     }
     __syncthreads();
     for (int cc = threadIdx.x; cc < dim; cc += 256) {
       float sum = 0.f;
-#pragma unroll
-      for (int w = 0; w < 8; ++w) sum += red[w][cc];
+      for (int w = 0; w < RL; ++w) sum += gate_red[w * dim + cc];
       atomicAdd(dfilm + b * dfilm_bs + g * film_gs + pass * dim + cc, sum);
     }
   }
@@ -316,22 +315,69 @@ __global__ void __launch_bounds__(256) accum_bf16_kernel(float4* __restrict__ ac
   }
 }
 
-// dW[r, c] += sum_b dfilm[b, r] * t[b, c]   (FiLM projection weights, contraction over the batch only)
+// dW[r, c] (+)= sum_b dfilm[b, r] * t[b, c]   (FiLM projection weights, contraction over the batch only).
+// HBM-bound on the dW stream (rows x cols fp32, > 1 GB at cfg3): one CTA owns a 64-row x 256-column tile, both operand
+// slices sit in shared memory, every thread keeps 16 rows x 4 columns of accumulators (5 shared loads per 64 FMAs) and
+// writes 128-bit rows.  ACCUM = 0 writes dW without reading it (fresh gradient buffer: one pass over dW instead of
+// zero-fill + read + write).
+template <bool ACCUM>
 __global__ void __launch_bounds__(256) film_wgrad_kernel(const float* __restrict__ dfilm, const float* __restrict__ t,
                                                          int batch, long long rows, int cols, float* __restrict__ dw) {
-  extern __shared__ float ts[];  // [batch][256] slice of t
+  extern __shared__ __align__(16) float fw_smem[];
+  float* ts = fw_smem;                 // [batch][256] slice of t
+  float* ds = fw_smem + batch * 256;   // [batch][64]  slice of dfilm
   const int c0 = blockIdx.x * 256;
+  const long long r0 = static_cast<long long>(blockIdx.y) * 64;
   for (int i = threadIdx.x; i < batch * 256; i += 256) {
-    const int b = i / 256, c = i - b * 256;
-    ts[i] = (c0 + c < cols) ? t[static_cast<long long>(b) * cols + c0 + c] : 0.f;
+    const int b = i >> 8, c = i & 255;
+    ts[i] = (c0 + c < cols) ? __ldg(t + static_cast<long long>(b) * cols + c0 + c) : 0.f;
+  }
+  for (int i = threadIdx.x; i < batch * 64; i += 256) {
+    const int b = i >> 6, r = i & 63;
+    ds[i] = (r0 + r < rows) ? __ldg(dfilm + b * rows + r0 + r) : 0.f;
   }
   __syncthreads();
-  const int c = c0 + threadIdx.x;
-  const long long r0 = static_cast<long long>(blockIdx.y) * 64;
-  for (long long r = r0; r < r0 + 64 && r < rows; ++r) {
-    float acc = 0.f;
-    for (int b = 0; b < batch; ++b) acc = fmaf(__ldg(dfilm + b * rows + r), ts[b * 256 + threadIdx.x], acc);
-    if (c < cols) dw[r * cols + c] += acc;
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;   // 4 columns at 4*tx, 16 rows at 16*ty
+  float acc[16][4];
+#pragma unroll
+  for (int i = 0; i < 16; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int b = 0; b < batch; ++b) {
+    const float4 tv = *reinterpret_cast<const float4*>(ts + b * 256 + 4 * tx);
+    float dv[16];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float4 d4 = *reinterpret_cast<const float4*>(ds + b * 64 + ty * 16 + 4 * q);
+      dv[4 * q] = d4.x; dv[4 * q + 1] = d4.y; dv[4 * q + 2] = d4.z; dv[4 * q + 3] = d4.w;
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      acc[i][0] = fmaf(dv[i], tv.x, acc[i][0]);
+      acc[i][1] = fmaf(dv[i], tv.y, acc[i][1]);
+      acc[i][2] = fmaf(dv[i], tv.z, acc[i][2]);
+      acc[i][3] = fmaf(dv[i], tv.w, acc[i][3]);
+    }
+  }
+  const int c = c0 + 4 * tx;
+  const bool vec = (c + 3 < cols) && (cols % 4 == 0);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const long long r = r0 + ty * 16 + i;
+    if (r >= rows) break;
+    float* o = dw + r * cols + c;
+    if (vec) {
+      float4 v = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+      if (ACCUM) {
+        const float4 old = *reinterpret_cast<const float4*>(o);
+        v.x += old.x; v.y += old.y; v.z += old.z; v.w += old.w;
+      }
+      *reinterpret_cast<float4*>(o) = v;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (c + j < cols) o[j] = ACCUM ? o[j] + acc[i][j] : acc[i][j];
+    }
   }
 }
 
@@ -391,19 +437,12 @@ extern "C" int ns2_wavenet_gate_bwd(const void* c_bf16, int64_t c_row_stride, co
               "wavenet_gate_bwd: bad arguments");
   NS2_REQUIRE(dim % 128 == 0 && dim <= 1024 && c_row_stride % 4 == 0 && dy_row_stride % 4 == 0 && dc_row_stride % 4 == 0,
               "wavenet_gate_bwd: dim must be a multiple of 128 (<= 1024), strides multiples of 4");
-  const unsigned grid = batches * ((rows_per_batch + 31) / 32) * groups;
-#define NS2_CASE(V)                                                                                                 \
-  case V:                                                                                                           \
-    wavenet_gate_bwd_kernel<V><<<grid, 256, 0, stream>>>(                                                           \
-        reinterpret_cast<const uint2*>(c_bf16), c_row_stride / 4, reinterpret_cast<const uint2*>(dy_bf16),          \
-        dy_row_stride / 4, reinterpret_cast<uint2*>(dc_bf16), dc_row_stride / 4, rows_per_batch, dim, groups, film, \
-        film_batch_stride, film_group_stride, dfilm, dfilm_batch_stride);                                           \
-    break;
-  switch (dim / 128) {
-    NS2_CASE(1) NS2_CASE(2) NS2_CASE(3) NS2_CASE(4) NS2_CASE(5) NS2_CASE(6) NS2_CASE(7) NS2_CASE(8)
-    default: return set_error(kErrInvalidArg, "wavenet_gate_bwd: unsupported dim %d", dim);
-  }
-#undef NS2_CASE
+  const unsigned grid = batches * ((rows_per_batch + 63) / 64) * groups;
+  const int row_lanes = 256 / (dim / 4);
+  wavenet_gate_bwd_kernel<<<grid, 256, static_cast<size_t>(row_lanes) * dim * sizeof(float), stream>>>(
+      reinterpret_cast<const uint2*>(c_bf16), c_row_stride / 4, reinterpret_cast<const uint2*>(dy_bf16), dy_row_stride / 4,
+      reinterpret_cast<uint2*>(dc_bf16), dc_row_stride / 4, rows_per_batch, dim, groups, film, film_batch_stride,
+      film_group_stride, dfilm, dfilm_batch_stride);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   NS2_CUDA_CHECK(cudaGetLastError());
   return kOk;
@@ -453,11 +492,14 @@ extern "C" int ns2_accum_bf16(float* acc, const void* t_bf16, int64_t count, voi
 }
 
 extern "C" int ns2_film_wgrad(const float* dfilm, const float* t, int32_t batch, int64_t rows, int32_t cols, float* dw,
-                              ns2_stream_t stream_) {
-  NS2_REQUIRE(dfilm && t && dw && batch > 0 && batch <= 48 && rows > 0 && cols > 0, "film_wgrad: bad arguments (batch <= 48)");
+                              int32_t accumulate, ns2_stream_t stream_) {
+  NS2_REQUIRE(dfilm && t && dw && batch > 0 && batch <= 32 && rows > 0 && cols > 0, "film_wgrad: bad arguments (batch <= 32)");
+  NS2_REQUIRE((reinterpret_cast<uintptr_t>(dw) & 15) == 0, "film_wgrad: dw must be 16-byte aligned");
   dim3 grid((cols + 255) / 256, static_cast<unsigned>((rows + 63) / 64));
-  film_wgrad_kernel<<<grid, 256, batch * 256 * sizeof(float), static_cast<cudaStream_t>(stream_)>>>(dfilm, t, batch, rows,
-                                                                                                    cols, dw);
+  const size_t smem = static_cast<size_t>(batch) * (256 + 64) * sizeof(float);
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  if (accumulate) film_wgrad_kernel<true><<<grid, 256, smem, st>>>(dfilm, t, batch, rows, cols, dw);
+  else film_wgrad_kernel<false><<<grid, 256, smem, st>>>(dfilm, t, batch, rows, cols, dw);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   NS2_CUDA_CHECK(cudaGetLastError());
   return kOk;

@@ -674,8 +674,9 @@ def mse_bwd(pred, target, coef, out_bf=None, out_f32=None):
     return out_bf if out_bf is not None else out_f32
 
 
-def film_wgrad(dfilm, t, dw):
-    """dw (rows, cols) f32 += dfilm (B, rows)^T @ t (B, cols)."""
+def film_wgrad(dfilm, t, dw, accumulate: bool = True):
+    """dw (rows, cols) f32 (+)= dfilm (B, rows)^T @ t (B, cols).  accumulate=False overwrites dw (which then need not be
+    initialised: one pass over the gradient buffer instead of zero-fill + read-modify-write)."""
     lib = _lib.load()
     for name, x in (("dfilm", dfilm), ("t", t), ("dw", dw)):
         _req(x, torch.float32, name)
@@ -684,7 +685,7 @@ def film_wgrad(dfilm, t, dw):
     B, rows = dfilm.shape
     for b0 in range(0, B, 32):
         check(lib.ns2_film_wgrad(dfilm[b0:b0 + 32].data_ptr(), t[b0:b0 + 32].data_ptr(), min(32, B - b0), rows, t.shape[1],
-                                 dw.data_ptr(), _stream(dw)), "ns2_film_wgrad")
+                                 dw.data_ptr(), int(accumulate or b0 > 0), _stream(dw)), "ns2_film_wgrad")
     return dw
 
 

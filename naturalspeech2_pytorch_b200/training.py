@@ -367,7 +367,7 @@ def train_backward(model, S: dict, d_out: torch.Tensor, reducer=None) -> Dict[st
 
     # ---- FiLM projections (one stacked matrix) and the timestep embedding ----
     rows = film.shape[1]
-    dWf = ops.film_wgrad(dfilm, S["t"].contiguous(), z(rows, model.dim_cond))
+    dWf = ops.film_wgrad(dfilm, S["t"].contiguous(), torch.empty(rows, model.dim_cond, device=dev), accumulate=False)
     dbf = dfilm.sum(0)
     dfilm_bf = ops.cast_bf16(dfilm, e(1, B, rows))
     dt = ops.gemm(dfilm_bf, T["film_w"], e(1, B, model.dim_cond, dt=torch.float32), n=model.dim_cond, epilogue=ops.EPI_F32)[0]

@@ -131,6 +131,9 @@ def test_small_reductions():
     dw = torch.ones(700, 300, device="cuda")
     ops.film_wgrad(dfilm, tt, dw)
     _close(dw, 1 + dfilm.t() @ tt, 1e-3, 1e-4, "film_wgrad")
+    dw2 = torch.full_like(dw, float("nan"))                    # overwrite mode never reads the buffer
+    ops.film_wgrad(dfilm, tt, dw2, accumulate=False)
+    _close(dw2, dfilm.t() @ tt, 1e-3, 1e-4, "film_wgrad overwrite")
 
 
 @pytest.mark.parametrize("B,H,Nq,Nk", [(1, 1, 128, 128), (2, 4, 1024, 1024), (2, 2, 200, 300), (2, 8, 256, 32), (1, 2, 32, 135)])
