@@ -12,6 +12,10 @@ namespace ns2 {
 
 std::atomic<long long> g_launches{0};
 
+// CTAs per SM of the streaming RMSNorm grid: 76 registers -> 3 resident, two generations measured best on B200
+// (19.5 us vs 20.1 at 3, 20.5 at 4, 23.3 for one CTA per 8 rows; 32768 x 512 rows, profiles/r02j_rmsnorm_stream.txt)
+constexpr int kRmsnormCtasPerSm = 6;
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -68,6 +72,73 @@ __global__ void __launch_bounds__(256) rmsnorm_kernel(const float* __restrict__ 
   }
 }
 
+// Streaming variant for large row counts: a resident grid (a few CTAs per SM), every warp walks rows
+// warp, warp + #warps, ... and issues the loads of its NEXT row before reducing / scaling / storing the current one, so
+// each warp always has one row (dim * 4 bytes) in flight.  The one-row-per-warp kernel above leaves the memory
+// pipe idle while a warp reduces, fetches its FiLM vectors and stores, and between CTA generations: ncu showed
+// 2.9 TB/s of DRAM reads at 53 % active warps (profiles/r02g_rmsnorm_ncu.txt).
+template <int VEC, bool OUT_BF16>
+__global__ void __launch_bounds__(256) rmsnorm_stream_kernel(const float* __restrict__ x, long long x_rs,
+                                                             long long rows, int dim, int rows_per_batch,
+                                                             const float* __restrict__ gamma,
+                                                             const float* __restrict__ film, long long film_bs,
+                                                             void* __restrict__ out, long long out_rs) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long nwarps = static_cast<long long>(gridDim.x) * 8;
+  long long row = static_cast<long long>(blockIdx.x) * 8 + warp;
+  if (row >= rows) return;
+  float4 cur[VEC], nxt[VEC];
+  {
+    const float4* xp = reinterpret_cast<const float4*>(x + row * x_rs);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) cur[i] = __ldg(xp + i * 32 + lane);
+  }
+  const float sqrt_dim = sqrtf(static_cast<float>(dim));
+  while (true) {
+    const long long nrow = row + nwarps;
+    const bool has_next = nrow < rows;
+    if (has_next) {
+      const float4* xp = reinterpret_cast<const float4*>(x + nrow * x_rs);
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) nxt[i] = __ldg(xp + i * 32 + lane);
+    }
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i)
+      ss += cur[i].x * cur[i].x + cur[i].y * cur[i].y + cur[i].z * cur[i].z + cur[i].w * cur[i].w;
+    ss = warp_sum(ss);
+    const float inv = sqrt_dim / fmaxf(sqrtf(ss), 1e-12f);   // F.normalize eps, then * sqrt(dim)   (ns2.py:738)
+    const float* fg = nullptr;
+    if (film != nullptr) fg = film + (row / rows_per_batch) * film_bs;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      const int c4 = i * 32 + lane;
+      float4 o = make_float4(cur[i].x * inv, cur[i].y * inv, cur[i].z * inv, cur[i].w * inv);
+      if (gamma != nullptr) {
+        const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + c4);
+        o.x *= g.x; o.y *= g.y; o.z *= g.z; o.w *= g.w;
+      }
+      if (fg != nullptr) {
+        const float4 g = __ldg(reinterpret_cast<const float4*>(fg) + c4);
+        const float4 b = __ldg(reinterpret_cast<const float4*>(fg + dim) + c4);
+        o.x = o.x * g.x + b.x; o.y = o.y * g.y + b.y; o.z = o.z * g.z + b.z; o.w = o.w * g.w + b.w;
+      }
+      if constexpr (OUT_BF16) {
+        uint2 w;
+        w.x = pack_bf16x2(o.x, o.y);
+        w.y = pack_bf16x2(o.z, o.w);
+        reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(out) + row * out_rs)[c4] = w;
+      } else {
+        reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + row * out_rs)[c4] = o;
+      }
+    }
+    if (!has_next) break;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) cur[i] = nxt[i];
+    row = nrow;
+  }
+}
+
 template <bool OUT_BF16>
 static int launch_rmsnorm(const float* x, long long x_rs, long long rows, int dim, int rows_per_batch,
                           const float* gamma, const float* film, long long film_bs, void* out,
@@ -76,10 +147,18 @@ static int launch_rmsnorm(const float* x, long long x_rs, long long rows, int di
   NS2_REQUIRE(dim % 128 == 0 && dim <= 1024, "rmsnorm: dim=%d must be a multiple of 128, <= 1024", dim);
   NS2_REQUIRE(x_rs % 4 == 0 && out_rs % 4 == 0 && film_bs % 4 == 0, "rmsnorm: strides must be 16B-aligned");
   const unsigned grid = static_cast<unsigned>((rows + 7) / 8);
+  // large problems: a few CTAs per SM, every warp walks >= 4 rows with next-row prefetch
+  unsigned sgrid = static_cast<unsigned>(num_sms() * kRmsnormCtasPerSm);
+  if (sgrid > grid / 4) sgrid = grid / 4;
+  const bool stream_variant = grid >= static_cast<unsigned>(8 * num_sms());
 #define NS2_RMS_CASE(V)                                                                         \
   case V:                                                                                       \
-    rmsnorm_kernel<V, OUT_BF16><<<grid, 256, 0, stream>>>(x, x_rs, rows, dim, rows_per_batch,   \
-                                                          gamma, film, film_bs, out, out_rs);   \
+    if (stream_variant)                                                                         \
+      rmsnorm_stream_kernel<V, OUT_BF16><<<sgrid, 256, 0, stream>>>(x, x_rs, rows, dim, rows_per_batch, gamma, film, \
+                                                                    film_bs, out, out_rs);      \
+    else                                                                                        \
+      rmsnorm_kernel<V, OUT_BF16><<<grid, 256, 0, stream>>>(x, x_rs, rows, dim, rows_per_batch, \
+                                                            gamma, film, film_bs, out, out_rs); \
     break;
   switch (dim / 128) {
     NS2_RMS_CASE(1) NS2_RMS_CASE(2) NS2_RMS_CASE(3) NS2_RMS_CASE(4) NS2_RMS_CASE(5) NS2_RMS_CASE(6)

@@ -13,7 +13,7 @@ B, N, D, H, Di, Dp = 32, 1024, 512, 8, 1365, 1408
 dev = "cuda"
 bf = torch.bfloat16
 which = set(sys.argv[1:]) or {"conv", "attn", "wavenet", "ffin", "ffout", "qkv", "norm", "rvq"}
-reps = 3
+reps = int(__import__("os").environ.get("NS2_PROF_REPS", "3"))
 import os  # noqa: E402
 FLAGS = int(os.environ.get("NS2_GEMM_FLAGS", "0"))   # 1 = mainloop only (NS2_GEMM_FLAG_SKIP_EPILOGUE)
 _gemm = ops.gemm
