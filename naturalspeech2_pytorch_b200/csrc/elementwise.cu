@@ -22,6 +22,46 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
+// One row of RMSNorm(+gamma)(+FiLM) held in a warp's registers: reduction, scale, store.  Shared by both kernels below
+// with the floating-point operation order pinned by explicit fmaf (no compiler-chosen contraction), so a row's result
+// does not depend on which kernel variant - i.e. on the problem size - produced it.
+template <int VEC, bool OUT_BF16>
+__device__ __forceinline__ void rmsnorm_row(const float4 (&v)[VEC], long long row, int lane, int dim, float sqrt_dim,
+                                            int rows_per_batch, const float* __restrict__ gamma,
+                                            const float* __restrict__ film, long long film_bs,
+                                            void* __restrict__ out, long long out_rs) {
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) ss = fmaf(v[i].x, v[i].x, fmaf(v[i].y, v[i].y, fmaf(v[i].z, v[i].z, fmaf(v[i].w, v[i].w, ss))));
+  ss = warp_sum(ss);
+  // F.normalize: x / max(||x||, eps), eps = 1e-12; then * sqrt(dim)   (ns2.py:738)
+  const float inv = __fdiv_rn(sqrt_dim, fmaxf(sqrtf(ss), 1e-12f));
+  const float* fg = nullptr;
+  if (film != nullptr) fg = film + (row / rows_per_batch) * film_bs;
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    const int c4 = i * 32 + lane;
+    float4 o = make_float4(__fmul_rn(v[i].x, inv), __fmul_rn(v[i].y, inv), __fmul_rn(v[i].z, inv), __fmul_rn(v[i].w, inv));
+    if (gamma != nullptr) {
+      const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + c4);
+      o.x = __fmul_rn(o.x, g.x); o.y = __fmul_rn(o.y, g.y); o.z = __fmul_rn(o.z, g.z); o.w = __fmul_rn(o.w, g.w);
+    }
+    if (fg != nullptr) {
+      const float4 g = __ldg(reinterpret_cast<const float4*>(fg) + c4);
+      const float4 b = __ldg(reinterpret_cast<const float4*>(fg + dim) + c4);
+      o.x = fmaf(o.x, g.x, b.x); o.y = fmaf(o.y, g.y, b.y); o.z = fmaf(o.z, g.z, b.z); o.w = fmaf(o.w, g.w, b.w);
+    }
+    if constexpr (OUT_BF16) {
+      uint2 w;
+      w.x = pack_bf16x2(o.x, o.y);
+      w.y = pack_bf16x2(o.z, o.w);
+      reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(out) + row * out_rs)[c4] = w;
+    } else {
+      reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + row * out_rs)[c4] = o;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // RMSNorm (+gamma) (+FiLM): one warp per row, the row stays in registers between the reduction and the
 // scaled write (single HBM read of x, single write of the result).  DIM = 32 * 4 * VEC.
@@ -37,39 +77,10 @@ __global__ void __launch_bounds__(256) rmsnorm_kernel(const float* __restrict__ 
   if (row >= rows) return;
   const float4* xp = reinterpret_cast<const float4*>(x + row * x_rs);
   float4 v[VEC];
-  float ss = 0.f;
 #pragma unroll
-  for (int i = 0; i < VEC; ++i) {
-    v[i] = __ldg(xp + i * 32 + lane);
-    ss += v[i].x * v[i].x + v[i].y * v[i].y + v[i].z * v[i].z + v[i].w * v[i].w;
-  }
-  ss = warp_sum(ss);
-  // F.normalize: x / max(||x||, eps), eps = 1e-12; then * sqrt(dim)   (ns2.py:738)
-  const float inv = sqrtf(static_cast<float>(dim)) / fmaxf(sqrtf(ss), 1e-12f);
-  const float* fg = nullptr;
-  if (film != nullptr) fg = film + (row / rows_per_batch) * film_bs;
-#pragma unroll
-  for (int i = 0; i < VEC; ++i) {
-    const int c4 = i * 32 + lane;
-    float4 o = make_float4(v[i].x * inv, v[i].y * inv, v[i].z * inv, v[i].w * inv);
-    if (gamma != nullptr) {
-      const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + c4);
-      o.x *= g.x; o.y *= g.y; o.z *= g.z; o.w *= g.w;
-    }
-    if (fg != nullptr) {
-      const float4 g = __ldg(reinterpret_cast<const float4*>(fg) + c4);
-      const float4 b = __ldg(reinterpret_cast<const float4*>(fg + dim) + c4);
-      o.x = o.x * g.x + b.x; o.y = o.y * g.y + b.y; o.z = o.z * g.z + b.z; o.w = o.w * g.w + b.w;
-    }
-    if constexpr (OUT_BF16) {
-      uint2 w;
-      w.x = pack_bf16x2(o.x, o.y);
-      w.y = pack_bf16x2(o.z, o.w);
-      reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(out) + row * out_rs)[c4] = w;
-    } else {
-      reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + row * out_rs)[c4] = o;
-    }
-  }
+  for (int i = 0; i < VEC; ++i) v[i] = __ldg(xp + i * 32 + lane);
+  rmsnorm_row<VEC, OUT_BF16>(v, row, lane, dim, sqrtf(static_cast<float>(dim)), rows_per_batch, gamma, film, film_bs, out,
+                             out_rs);
 }
 
 // Streaming variant for large row counts: a resident grid (a few CTAs per SM), every warp walks rows
@@ -102,36 +113,7 @@ __global__ void __launch_bounds__(256) rmsnorm_stream_kernel(const float* __rest
 #pragma unroll
       for (int i = 0; i < VEC; ++i) nxt[i] = __ldg(xp + i * 32 + lane);
     }
-    float ss = 0.f;
-#pragma unroll
-    for (int i = 0; i < VEC; ++i)
-      ss += cur[i].x * cur[i].x + cur[i].y * cur[i].y + cur[i].z * cur[i].z + cur[i].w * cur[i].w;
-    ss = warp_sum(ss);
-    const float inv = sqrt_dim / fmaxf(sqrtf(ss), 1e-12f);   // F.normalize eps, then * sqrt(dim)   (ns2.py:738)
-    const float* fg = nullptr;
-    if (film != nullptr) fg = film + (row / rows_per_batch) * film_bs;
-#pragma unroll
-    for (int i = 0; i < VEC; ++i) {
-      const int c4 = i * 32 + lane;
-      float4 o = make_float4(cur[i].x * inv, cur[i].y * inv, cur[i].z * inv, cur[i].w * inv);
-      if (gamma != nullptr) {
-        const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + c4);
-        o.x *= g.x; o.y *= g.y; o.z *= g.z; o.w *= g.w;
-      }
-      if (fg != nullptr) {
-        const float4 g = __ldg(reinterpret_cast<const float4*>(fg) + c4);
-        const float4 b = __ldg(reinterpret_cast<const float4*>(fg + dim) + c4);
-        o.x = o.x * g.x + b.x; o.y = o.y * g.y + b.y; o.z = o.z * g.z + b.z; o.w = o.w * g.w + b.w;
-      }
-      if constexpr (OUT_BF16) {
-        uint2 w;
-        w.x = pack_bf16x2(o.x, o.y);
-        w.y = pack_bf16x2(o.z, o.w);
-        reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(out) + row * out_rs)[c4] = w;
-      } else {
-        reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + row * out_rs)[c4] = o;
-      }
-    }
+    rmsnorm_row<VEC, OUT_BF16>(cur, row, lane, dim, sqrt_dim, rows_per_batch, gamma, film, film_bs, out, out_rs);
     if (!has_next) break;
 #pragma unroll
     for (int i = 0; i < VEC; ++i) cur[i] = nxt[i];
@@ -180,7 +162,7 @@ __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + expf(-x));
 
 // If `freqs` is non-NULL the input row is the learned-sinusoidal embedding of x[b] (a scalar time):
 // [t, sin(2 pi t w_0..half-1), cos(2 pi t w_0..half-1)], k = 2*half + 1   (ns2.py:108-120).
-__global__ void __launch_bounds__(256) small_linear_kernel(const float* __restrict__ x, long long x_rs,
+__global__ void __launch_bounds__(1024) small_linear_kernel(const float* __restrict__ x, long long x_rs,
                                                            int batch, int k,
                                                            const float* __restrict__ freqs,
                                                            const float* __restrict__ W,
@@ -206,7 +188,7 @@ __global__ void __launch_bounds__(256) small_linear_kernel(const float* __restri
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int j = blockIdx.x * 8 + warp;
+  const int j = blockIdx.x * (blockDim.x >> 5) + warp;   // one warp per output feature
   if (j >= n_out) return;
   const float* w = W + static_cast<long long>(j) * k;
   for (int b0 = 0; b0 < batch; b0 += 8) {
@@ -714,7 +696,9 @@ int ns2_time_cond(const float* times, int32_t batch, const float* freqs, int32_t
   const size_t smem = static_cast<size_t>(batch) * k * sizeof(float);
   NS2_REQUIRE(smem <= 200 * 1024, "time_cond: batch*k=%d too large for shared memory", batch * k);
   NS2_CUDA_CHECK(configure_small_linear());
-  small_linear_kernel<<<(n_out + 7) / 8, 256, smem, static_cast<cudaStream_t>(stream)>>>(
+  // every CTA rebuilds the (batch, k) sinusoidal embedding in shared memory (precise sinf / cosf): 32 output features
+  // per 1024-thread CTA = one wave of 64 CTAs at n_out = 2048 instead of two waves of 8-feature CTAs (77 -> ~20 us)
+  small_linear_kernel<<<(n_out + 31) / 32, 1024, smem, static_cast<cudaStream_t>(stream)>>>(
       times, 1, batch, k, freqs, W, bias, n_out, /*SiLU*/ 1, out, out_row_stride);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   NS2_CUDA_CHECK(cudaGetLastError());
