@@ -42,6 +42,15 @@ def test_argument_validation_without_gpu(lib):
     t = AttnArgs()
     assert lib.ns2_attn_fwd(ctypes.byref(t), None) < 0
     assert lib.ns2_rvq_encode(None, 0, 128, None, None, None, None, 8, 1024, None, None, None) < 0
+    # round-2 entry points (aligner / conditioning encoders): size checks come before any CUDA call too
+    assert lib.ns2_maximum_path_workspace_bytes(32, 100, 1024) == 32 * 1024 * 128
+    assert lib.ns2_maximum_path(1, 1, 2, 2000, 16, float("-inf"), 1, 1 << 20, 1, None, None) < 0
+    assert b"1024" in lib.ns2_last_error()
+    assert lib.ns2_maximum_path(None, None, 0, 10, 10, float("-inf"), None, 0, None, None, None) == 0   # empty batch
+    assert lib.ns2_groupnorm_silu(None, 2, 8, 100, 8, None, None, 1e-5, None, None, None, None) < 0       # 100 % 8 != 0
+    assert lib.ns2_rowdot(None, 4, 10, None, None, 0, None, None) < 0                                     # dim % 4 != 0
+    assert lib.ns2_embedding_bf16(None, 4, None, 10, 128, 10, None, None) < 0                             # pad_id outside
+    assert lib.ns2_film_wgrad(None, None, 33, 8, 8, None, 0, None) < 0
 
 
 def test_struct_layout_matches_header():
