@@ -28,6 +28,11 @@ typedef void* ns2_stream_t; /* cudaStream_t */
 
 const char* ns2_last_error(void);
 int ns2_abi_version(void);
+/* Size the persistent grids of every kernel for at most `sms` SMs (rounded down to an even count; 0 = all SMs, the
+ * default).  The GEMM / attention kernels run one CTA (pair) per SM for the whole launch, so a concurrent kernel that
+ * holds a few SMs - NCCL's all-reduce of the gradients during the backward pass (ns2.py:1723-1726, 1886) - would delay
+ * whole CTAs by a full tile loop; leaving those SMs out of the grid avoids that.  Returns the previous limit. */
+int ns2_set_sm_limit(int sms);
 
 /* ------------------------------------------------------------------------------------------------
  * 1. Segmented tcgen05 GEMM with fused epilogues.
@@ -345,7 +350,9 @@ int ns2_colsum_bf16(const void* t_bf16, int64_t rows, int32_t cols, int64_t row_
 int ns2_group_sum_bf16(const void* t_bf16, int64_t rows, int32_t dim, int32_t groups, void* out_bf16, ns2_stream_t stream);
 int ns2_mse_bwd(const float* pred, const float* target, const float* coef, int32_t batch, int64_t per_sample,
                 void* out_bf16 /* optional */, float* out_f32 /* optional */, ns2_stream_t stream);
-int ns2_film_wgrad(const float* dfilm, const float* t, int32_t batch, int64_t rows, int32_t cols, float* dw,
+int ns2_film_wgrad(const float* dfilm, int64_t dfilm_batch_stride /* elements between batch rows of dfilm (>= rows): a
+                   column window of the stacked FiLM gradient can be reduced as soon as its layer is final */,
+                   const float* t, int32_t batch, int64_t rows, int32_t cols, float* dw,
                    int32_t accumulate /* 0: dw = ..., dw need not be initialised; 1: dw += ... */, ns2_stream_t stream);
 /*    ns2_accum_bf16       : acc (f32) += t (bf16); acc_bf16 (optional) = bf16(acc)   (joins a branch gradient) */
 int ns2_accum_bf16(float* acc, const void* t_bf16, int64_t count, void* acc_bf16, ns2_stream_t stream);

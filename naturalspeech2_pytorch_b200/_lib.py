@@ -86,6 +86,7 @@ _P, _I32, _I64, _F = C.c_void_p, C.c_int32, C.c_int64, C.c_float
 SIGNATURES = {
     "ns2_last_error": (C.c_char_p, []),
     "ns2_abi_version": (C.c_int, []),
+    "ns2_set_sm_limit": (C.c_int, [C.c_int]),
     "ns2_launch_count": (C.c_int64, []),
     "ns2_gemm": (C.c_int, [C.POINTER(GemmArgs), _P]),
     "ns2_wgrad": (C.c_int, [C.POINTER(WgradArgs), _P]),
@@ -115,7 +116,7 @@ SIGNATURES = {
     "ns2_colsum_bf16": (C.c_int, [_P, _I64, _I32, _I64, _P, _P]),
     "ns2_group_sum_bf16": (C.c_int, [_P, _I64, _I32, _I32, _P, _P]),
     "ns2_mse_bwd": (C.c_int, [_P, _P, _P, _I32, _I64, _P, _P, _P]),
-    "ns2_film_wgrad": (C.c_int, [_P, _P, _I32, _I64, _I32, _P, _I32, _P]),
+    "ns2_film_wgrad": (C.c_int, [_P, _I64, _P, _I32, _I64, _I32, _P, _I32, _P]),
     "ns2_accum_bf16": (C.c_int, [_P, _P, _I64, _P, _P]),
     "ns2_rvq_prepare": (C.c_int, [_P, _I32, _I32, _I32, _P, _P, _P, _P]),
     "ns2_rvq_encode": (C.c_int, [_P, _I64, _I32, _P, _P, _P, _P, _I32, _I32, _P, _P, _P]),

@@ -321,8 +321,9 @@ __global__ void __launch_bounds__(256) accum_bf16_kernel(float4* __restrict__ ac
 // writes 128-bit rows.  ACCUM = 0 writes dW without reading it (fresh gradient buffer: one pass over dW instead of
 // zero-fill + read + write).
 template <bool ACCUM>
-__global__ void __launch_bounds__(256) film_wgrad_kernel(const float* __restrict__ dfilm, const float* __restrict__ t,
-                                                         int batch, long long rows, int cols, float* __restrict__ dw) {
+__global__ void __launch_bounds__(256) film_wgrad_kernel(const float* __restrict__ dfilm, long long dfilm_bs,
+                                                         const float* __restrict__ t, int batch, long long rows, int cols,
+                                                         float* __restrict__ dw) {
   extern __shared__ __align__(16) float fw_smem[];
   float* ts = fw_smem;                 // [batch][256] slice of t
   float* ds = fw_smem + batch * 256;   // [batch][64]  slice of dfilm
@@ -334,7 +335,7 @@ __global__ void __launch_bounds__(256) film_wgrad_kernel(const float* __restrict
   }
   for (int i = threadIdx.x; i < batch * 64; i += 256) {
     const int b = i >> 6, r = i & 63;
-    ds[i] = (r0 + r < rows) ? __ldg(dfilm + b * rows + r0 + r) : 0.f;
+    ds[i] = (r0 + r < rows) ? __ldg(dfilm + b * dfilm_bs + r0 + r) : 0.f;
   }
   __syncthreads();
   const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;   // 4 columns at 4*tx, 16 rows at 16*ty
@@ -491,15 +492,16 @@ extern "C" int ns2_accum_bf16(float* acc, const void* t_bf16, int64_t count, voi
   return kOk;
 }
 
-extern "C" int ns2_film_wgrad(const float* dfilm, const float* t, int32_t batch, int64_t rows, int32_t cols, float* dw,
-                              int32_t accumulate, ns2_stream_t stream_) {
+extern "C" int ns2_film_wgrad(const float* dfilm, int64_t dfilm_batch_stride, const float* t, int32_t batch, int64_t rows,
+                              int32_t cols, float* dw, int32_t accumulate, ns2_stream_t stream_) {
   NS2_REQUIRE(dfilm && t && dw && batch > 0 && batch <= 32 && rows > 0 && cols > 0, "film_wgrad: bad arguments (batch <= 32)");
   NS2_REQUIRE((reinterpret_cast<uintptr_t>(dw) & 15) == 0, "film_wgrad: dw must be 16-byte aligned");
+  NS2_REQUIRE(dfilm_batch_stride >= rows, "film_wgrad: dfilm_batch_stride %lld < rows", static_cast<long long>(dfilm_batch_stride));
   dim3 grid((cols + 255) / 256, static_cast<unsigned>((rows + 63) / 64));
   const size_t smem = static_cast<size_t>(batch) * (256 + 64) * sizeof(float);
   cudaStream_t st = static_cast<cudaStream_t>(stream_);
-  if (accumulate) film_wgrad_kernel<true><<<grid, 256, smem, st>>>(dfilm, t, batch, rows, cols, dw);
-  else film_wgrad_kernel<false><<<grid, 256, smem, st>>>(dfilm, t, batch, rows, cols, dw);
+  if (accumulate) film_wgrad_kernel<true><<<grid, 256, smem, st>>>(dfilm, dfilm_batch_stride, t, batch, rows, cols, dw);
+  else film_wgrad_kernel<false><<<grid, 256, smem, st>>>(dfilm, dfilm_batch_stride, t, batch, rows, cols, dw);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   NS2_CUDA_CHECK(cudaGetLastError());
   return kOk;

@@ -78,6 +78,8 @@ int make_tmap_f32(CUtensorMap* out, const void* base, int rank, const uint64_t* 
 
 constexpr int kMaxDevices = 64;
 
+static std::atomic<int> g_sm_limit{0};   // ns2_set_sm_limit: 0 = use every SM
+
 int num_sms() {
   static std::atomic<int> cache[kMaxDevices];
   int dev = 0;
@@ -87,7 +89,8 @@ int num_sms() {
     if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
     cache[dev].store(n, std::memory_order_relaxed);
   }
-  return n;
+  const int lim = g_sm_limit.load(std::memory_order_relaxed);
+  return (lim > 0 && lim < n) ? lim : n;
 }
 
 cudaError_t set_max_smem_once_impl(const void* kernel, int bytes) {
@@ -109,4 +112,8 @@ cudaError_t set_max_smem_once_impl(const void* kernel, int bytes) {
 extern "C" {
 const char* ns2_last_error(void) { return ns2::last_error_cstr(); }
 int ns2_abi_version(void) { return NS2_ABI_VERSION; }
+int ns2_set_sm_limit(int sms) {
+  const int prev = ns2::g_sm_limit.exchange(sms < 0 ? 0 : (sms & ~1), std::memory_order_relaxed);
+  return prev;
+}
 }

@@ -42,6 +42,11 @@ def _req(t: torch.Tensor, dtype: torch.dtype, name: str) -> None:
         raise ValueError(f"{name} must be contiguous in its last dimension")
 
 
+def set_sm_limit(sms: int) -> int:
+    """Size every kernel's persistent grid for at most `sms` SMs (0 = all).  Returns the previous limit."""
+    return int(_lib.load().ns2_set_sm_limit(int(sms)))
+
+
 def launch_count() -> int:
     return int(_lib.load().ns2_launch_count())
 
@@ -676,16 +681,20 @@ def mse_bwd(pred, target, coef, out_bf=None, out_f32=None):
 
 def film_wgrad(dfilm, t, dw, accumulate: bool = True):
     """dw (rows, cols) f32 (+)= dfilm (B, rows)^T @ t (B, cols).  accumulate=False overwrites dw (which then need not be
-    initialised: one pass over the gradient buffer instead of zero-fill + read-modify-write)."""
+    initialised: one pass over the gradient buffer instead of zero-fill + read-modify-write).  `dfilm` may be a column
+    window of a wider (B, total_rows) buffer (unit column stride)."""
     lib = _lib.load()
     for name, x in (("dfilm", dfilm), ("t", t), ("dw", dw)):
         _req(x, torch.float32, name)
-        if not x.is_contiguous():
-            raise ValueError(f"{name} must be contiguous")
+    if not (t.is_contiguous() and dw.is_contiguous()) or dfilm.dim() != 2 or (dfilm.shape[1] > 1 and dfilm.stride(1) != 1):
+        raise ValueError("t and dw must be contiguous, dfilm (B, rows) with unit column stride")
     B, rows = dfilm.shape
+    if tuple(dw.shape) != (rows, t.shape[1]) or t.shape[0] != B:
+        raise ValueError("film_wgrad: inconsistent shapes")
     for b0 in range(0, B, 32):
-        check(lib.ns2_film_wgrad(dfilm[b0:b0 + 32].data_ptr(), t[b0:b0 + 32].data_ptr(), min(32, B - b0), rows, t.shape[1],
-                                 dw.data_ptr(), int(accumulate or b0 > 0), _stream(dw)), "ns2_film_wgrad")
+        check(lib.ns2_film_wgrad(dfilm[b0:b0 + 32].data_ptr(), dfilm.stride(0), t[b0:b0 + 32].data_ptr(), min(32, B - b0),
+                                 rows, t.shape[1], dw.data_ptr(), int(accumulate or b0 > 0), _stream(dw)),
+              "ns2_film_wgrad")
     return dw
 
 

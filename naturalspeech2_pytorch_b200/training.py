@@ -219,6 +219,7 @@ def train_backward(model, S: dict, d_out: torch.Tensor, reducer=None) -> Dict[st
     z = lambda *s: torch.zeros(*s, device=dev, dtype=torch.float32)
     grads: Dict[str, torch.Tensor] = {}
     dfilm = z(B, film.shape[1])
+    t_cond = S["t"].contiguous()
     dil = [2 ** i for i in range(G)]
 
     # ---- to_pred: Linear (no bias) after RMSNorm(gamma) ----
@@ -293,6 +294,12 @@ def train_backward(model, S: dict, d_out: torch.Tensor, reducer=None) -> Dict[st
         dh1 = ops.gemm(d_qkv, T[f"l{l}_qkv"], e(B, N, D), n=D, epilogue=ops.EPI_BF16)
         ops.rmsnorm_film_bwd(L["x_in"], dh1, dxr, dxr_bf, rows_per_batch=N, film=film[:, fo:fo + 2 * D],
                              dfilm=dfilm[:, fo:fo + 2 * D])
+        # FiLM projections of this layer's norms: their rows of dfilm are final now, so the weight gradient (the largest
+        # gradient buffers of the model) joins this layer's all-reduce instead of trailing the whole backward
+        dWl = ops.film_wgrad(dfilm[:, fo:fo + npl * 2 * D], t_cond, torch.empty(npl * 2 * D, model.dim_cond, device=dev),
+                             accumulate=False)
+        for k, idx in enumerate((0, 2, 4) if conditional else (0, 4)):
+            grads[pfx + f"{idx}.to_gamma_beta.weight"] = dWl[k * 2 * D:(k + 1) * 2 * D]
         flush()   # this layer's gradients are final: their all-reduce overlaps the layers still to come
 
     if conditional:
@@ -322,6 +329,10 @@ def train_backward(model, S: dict, d_out: torch.Tensor, reducer=None) -> Dict[st
         dy = dcy[:, :, G * D:]
         dc = dcy[:, :, :G * D]
         ops.wavenet_gate_bwd(c_pre, dy, dc, film[:, fo_s:], dfilm[:, fo_s:], dim=D, groups=G, film_group_stride=2 * D)
+        dWs = ops.film_wgrad(dfilm[:, fo_s:fo_s + G * 2 * D], t_cond, torch.empty(G * 2 * D, model.dim_cond, device=dev),
+                             accumulate=False)   # this stack's FiLM projections (see the transformer loop)
+        for g in range(G):
+            grads[f"wavenet.stacks.{s}.blocks.{g}.to_time_cond.weight"] = dWs[g * 2 * D:(g + 1) * 2 * D]
         dWp = z(G * D, 4 * D)
         for tap in range(3):
             ops.wgrad(dc, x_in, dWp[:, tap * D:(tap + 1) * D], n=D, k=D, shift_units=2 - tap, groups=G,
@@ -367,7 +378,6 @@ def train_backward(model, S: dict, d_out: torch.Tensor, reducer=None) -> Dict[st
 
     # ---- FiLM projections (one stacked matrix) and the timestep embedding ----
     rows = film.shape[1]
-    dWf = ops.film_wgrad(dfilm, S["t"].contiguous(), torch.empty(rows, model.dim_cond, device=dev), accumulate=False)
     dbf = dfilm.sum(0)
     dfilm_bf = ops.cast_bf16(dfilm, e(1, B, rows))
     dt = ops.gemm(dfilm_bf, T["film_w"], e(1, B, model.dim_cond, dt=torch.float32), n=model.dim_cond, epilogue=ops.EPI_F32)[0]
@@ -386,12 +396,12 @@ def train_backward(model, S: dict, d_out: torch.Tensor, reducer=None) -> Dict[st
     for s in range(nst):
         for g in range(G):
             key = f"wavenet.stacks.{s}.blocks.{g}.to_time_cond."
-            grads[key + "weight"], grads[key + "bias"] = dWf[off:off + 2 * D], dbf[off:off + 2 * D]
+            grads[key + "bias"] = dbf[off:off + 2 * D]
             off += 2 * D
     for l in range(model.depth):
         for idx in ((0, 2, 4) if conditional else (0, 4)):
             key = f"transformer.layers.{l}.{idx}.to_gamma_beta."
-            grads[key + "weight"], grads[key + "bias"] = dWf[off:off + 2 * D], dbf[off:off + 2 * D]
+            grads[key + "bias"] = dbf[off:off + 2 * D]
             off += 2 * D
     # (B,)-sized timestep embedding: torch autograd on a recomputation (ns2.py:108-120, 839-843)
     tc = model.to_time_cond

@@ -50,7 +50,7 @@ def test_argument_validation_without_gpu(lib):
     assert lib.ns2_groupnorm_silu(None, 2, 8, 100, 8, None, None, 1e-5, None, None, None, None) < 0       # 100 % 8 != 0
     assert lib.ns2_rowdot(None, 4, 10, None, None, 0, None, None) < 0                                     # dim % 4 != 0
     assert lib.ns2_embedding_bf16(None, 4, None, 10, 128, 10, None, None) < 0                             # pad_id outside
-    assert lib.ns2_film_wgrad(None, None, 33, 8, 8, None, 0, None) < 0
+    assert lib.ns2_film_wgrad(None, 8, None, 33, 8, 8, None, 0, None) < 0
 
 
 def test_struct_layout_matches_header():

@@ -134,6 +134,10 @@ def test_small_reductions():
     dw2 = torch.full_like(dw, float("nan"))                    # overwrite mode never reads the buffer
     ops.film_wgrad(dfilm, tt, dw2, accumulate=False)
     _close(dw2, dfilm.t() @ tt, 1e-3, 1e-4, "film_wgrad overwrite")
+    wide = torch.randn(40, 1000, device="cuda", generator=g)   # a column window of a wider gradient table (per-layer use)
+    dw3 = torch.empty(600, 300, device="cuda")
+    ops.film_wgrad(wide[:, 200:800], tt, dw3, accumulate=False)
+    _close(dw3, wide[:, 200:800].t() @ tt, 1e-3, 1e-4, "film_wgrad window")
 
 
 @pytest.mark.parametrize("B,H,Nq,Nk", [(1, 1, 128, 128), (2, 4, 1024, 1024), (2, 2, 200, 300), (2, 8, 256, 32), (1, 2, 32, 135)])
