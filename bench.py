@@ -70,7 +70,7 @@ def _peaks():
 def _ncu_traffic():
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the newest committed
     `ncu --set full` capture under profiles/ (not measured in this run: ncu cannot wrap a timed run)."""
-    for name in ("r02_dominant_kernel_ncu.json", "r01_dominant_kernel_ncu.json"):
+    for name in ("r02k_dominant_kernel_ncu.json", "r02_dominant_kernel_ncu.json", "r01_dominant_kernel_ncu.json"):
         p = ROOT / "profiles" / name
         if p.exists():
             d = json.loads(p.read_text())
