@@ -105,6 +105,8 @@ typedef struct ns2_gemm_args {
 #define NS2_GEMM_FLAG_SKIP_EPILOGUE 1  /* measurement aid: run the TMA/MMA mainloop only, write nothing (CTA-pair kernel) */
 #define NS2_GEMM_FLAG_SILU 4 /* BF16 / F32 epilogues: out = silu(acc + bias) (+ resid) — Conv1d + nn.SiLU of the prompt
                                encoder (ns2.py:316-320) and CausalConv1d + SiLU of the phoneme encoder (ns2.py:255-257) */
+#define NS2_GEMM_FLAG_NARROW_LAST 8 /* tuning / A-B tests (CTA-pair kernel, n % 256 != 0): schedule the partial-width n-tiles
+                                      after all full-width ones instead of n-fastest */
 #define NS2_GEMM_FLAG_WAVENET_ONE_PASS 2 /* tuning / A-B tests: WAVENET with two 256-column accumulators and a single epilogue pass */
 
 int ns2_gemm(const ns2_gemm_args* args, ns2_stream_t stream);

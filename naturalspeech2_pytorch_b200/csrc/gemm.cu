@@ -37,6 +37,7 @@ struct GemmDev {
   CUtensorMap tmOut;   // pair kernel: TMA store / reduce-add target (3-D: columns, positions, batch)
   int reduce_add;      // pair kernel, F32 epilogue with resid == out: out += acc + bias via TMA reduce-add
   int tiles_n, tiles_per_batch, tiles_m, num_tiles;
+  int narrow_last;     // pair kernel, groups == 1, n % BN != 0: schedule the partial-width n-tiles after all full-width ones
   int a_rows, n, groups;
   int a_gcs, b_grs, out_gcs;
   int dil[NS2_GEMM_MAX_GROUPS];
@@ -70,11 +71,30 @@ struct TileCoord {
 template <int ROWS>
 __device__ __forceinline__ TileCoord decode_tile(const GemmDev& p, int tile) {
   TileCoord t;
-  const int per_group = p.tiles_m * p.tiles_n;
-  t.g = tile / per_group;
-  const int r = tile - t.g * per_group;
-  const int m_tile = r / p.tiles_n;
-  t.n_tile = r - m_tile * p.tiles_n;
+  int m_tile;
+  if (p.narrow_last) {
+    // The last n-tile of every row block is narrower (n % BN columns) and its MMAs are cheaper.  With the plain
+    // n-fastest order and the static tile -> pair round robin those cheap tiles land on a subset of the pairs (FFN
+    // conv: tiles_n = 6, 74 pairs -> only odd pairs ever see one) and the launch still lasts ceil(tiles / pairs) FULL
+    // tiles.  Full-width tiles first (n fastest, so a row block's activations stay hot in L2), then all narrow ones:
+    // every pair ends on cheap tiles and the longest pair does 9 full + 2 narrow instead of 11 full (FFN conv, cfg2).
+    const int wide_n = p.tiles_n - 1;
+    const int wide_total = p.tiles_m * wide_n;
+    t.g = 0;
+    if (tile < wide_total) {
+      m_tile = tile / wide_n;
+      t.n_tile = tile - m_tile * wide_n;
+    } else {
+      m_tile = tile - wide_total;
+      t.n_tile = wide_n;
+    }
+  } else {
+    const int per_group = p.tiles_m * p.tiles_n;
+    t.g = tile / per_group;
+    const int r = tile - t.g * per_group;
+    m_tile = r / p.tiles_n;
+    t.n_tile = r - m_tile * p.tiles_n;
+  }
   t.b = m_tile / p.tiles_per_batch;
   t.n0 = (m_tile - t.b * p.tiles_per_batch) * ROWS;
   return t;
@@ -762,7 +782,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Gemm2Cfg<BN, NACC>::
       uint32_t it = 0;
       uint32_t ti = 0;
       for (int tile = pair; tile < p.num_tiles; tile += num_pairs, ++ti) {
-        const int n_tile = tile % p.tiles_n;
+        const int n_tile = decode_tile<2 * BM>(p, tile).n_tile;
         const int bn_eff = (p.n - n_tile * BN) < BN ? (p.n - n_tile * BN) : BN;
         const uint32_t idesc = umma_idesc_f16(2 * BM, bn_eff, /*bf16*/ 1, 0, 0);
         const uint32_t as = (Cfg::ACC_STAGES == 2) ? (ti & 1) : 0;
@@ -949,7 +969,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Gemm2Cfg<256, 1>::TH
       if (leader) {
         uint32_t it = 0, grp = 0;
         auto mma_phase = [&](int tile, int want_acc, uint32_t d_tmem) {
-          const int n_tile = tile % p.tiles_n;
+          const int n_tile = decode_tile<2 * BM>(p, tile).n_tile;
           const int bn_eff = (p.n - n_tile * BN) < BN ? (p.n - n_tile * BN) : BN;
           const uint32_t idesc = umma_idesc_f16(2 * BM, bn_eff, /*bf16*/ 1, 0, 0);
           uint32_t started = want_acc;   // phase 2 accumulates on top of the gate values from its first MMA on
@@ -1231,6 +1251,7 @@ extern "C" int ns2_gemm(const ns2_gemm_args* a, ns2_stream_t stream_) {
   dev.tiles_per_batch = (a->a_rows + tile_rows - 1) / tile_rows;
   dev.tiles_m = dev.tiles_per_batch * a->a_batches;
   dev.num_tiles = dev.tiles_m * dev.tiles_n * a->groups;
+  dev.narrow_last = ((a->flags & NS2_GEMM_FLAG_NARROW_LAST) && pair && a->groups == 1 && dev.tiles_n > 1 && a->n % bn != 0) ? 1 : 0;
   dev.a_rows = a->a_rows;
   dev.n = a->n;
   dev.groups = a->groups;
